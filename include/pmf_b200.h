@@ -1,0 +1,134 @@
+/*
+ * pmf_b200.h -- C-ABI of libpmf_b200.so: the B200 (sm_100a) training hot path for the
+ * probabilistic matrix-factorisation models of rogeliolopezcamara/prob-matrix-factorization.
+ *
+ * The reference has no FFI (it is pure Python); its "operator interface" for this path is
+ * the body of each model class's fit/predict/evaluate methods.  Every entry point below
+ * names the reference lines it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers + sizes; no torch / C++ types; all functions return int:
+ *     0 = PMF_OK, negative = error; pmf_last_error() gives the message (thread local).
+ *   - "d_" pointers are device memory owned by the caller (e.g. torch CUDA tensors);
+ *     "h_" pointers are host memory.  `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream).  No entry point synchronises unless it says so.
+ *   - factor tables are row-major float32 with a row stride `ld` (in floats) that is a
+ *     multiple of 8 (one 32-byte sector) and >= K; columns K..ld-1 are kept at zero.
+ *   - ids are int32; rating values float32.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef PMF_B200_H
+#define PMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMF_OK 0
+#define PMF_EINVAL (-1)   /* bad argument */
+#define PMF_ECUDA (-2)    /* CUDA runtime error */
+#define PMF_ENOMEM (-3)   /* allocation failed */
+#define PMF_EUNSUPPORTED (-4)
+
+/* ---- library ---------------------------------------------------------------------- */
+int pmf_version(void);                 /* 100*major + minor */
+const char* pmf_last_error(void);      /* message of the last failing call on this thread */
+int pmf_device_count(int* count);      /* fails (PMF_ECUDA) when no CUDA driver/device */
+int pmf_row_stride(int K);             /* smallest legal `ld` for K factors */
+/* Blocking device->host copy of `bytes` bytes (diagnostics / tests; synchronises the stream). */
+int pmf_copy_to_host(void* h_dst, const void* d_src, int64_t bytes, void* stream);
+/* Kernel-variant selection for experiments ("gamma_group", "gamma_unroll"; 0 = automatic). */
+int pmf_tune(const char* key, int value);
+
+/* ---- a1: observation grouping ("CSR build") ----------------------------------------
+ * Replaces _build_index_lists (poisson_mf_cavi.py:73-84, hpf_cavi.py:97-107,
+ * gaussian_mf_cavi.py:59-76, gaussian_mf_cavi_bias.py:69-86): observations grouped by row id,
+ * each row keeping ORIGINAL order (stable).  Bit-exact: perm == argsort(key, kind="stable").
+ *
+ * A pmf_csr is an opaque, library-owned device structure for ONE orientation:
+ *   row_ptr int32[n_rows+1], perm int32[nnz] (original observation index),
+ *   col int32[nnz] (id of the other side), val float32[nnz],
+ * plus the work decomposition used by the pass kernels: every row is cut into segments of
+ * at most seg_len observations (an empty row is one empty segment).
+ */
+typedef struct pmf_csr pmf_csr;
+
+/* d_key: ids to group by; d_other: ids of the other side; d_val: ratings; all length nnz,
+ * device memory.  Synchronises the stream before returning (sizes are data dependent). */
+int pmf_csr_build(const int32_t* d_key, const int32_t* d_other, const float* d_val,
+                  int64_t nnz, int32_t n_rows, int32_t seg_len, void* stream, pmf_csr** out);
+/* Copy of rows [row_begin,row_end) as a self-contained structure (row ids stay GLOBAL via
+ * pmf_csr_row_offset); used to shard the rating list by nonzero across GPUs. */
+int pmf_csr_slice(const pmf_csr* src, int32_t row_begin, int32_t row_end, void* stream, pmf_csr** out);
+int pmf_csr_free(pmf_csr* csr);
+int64_t pmf_csr_nnz(const pmf_csr* csr);
+int32_t pmf_csr_rows(const pmf_csr* csr);
+int32_t pmf_csr_row_offset(const pmf_csr* csr);
+int32_t pmf_csr_segments(const pmf_csr* csr);
+int32_t pmf_csr_multi_rows(const pmf_csr* csr);   /* rows cut into >1 segment */
+int32_t pmf_csr_seg_len(const pmf_csr* csr);
+const int32_t* pmf_csr_row_ptr(const pmf_csr* csr);  /* device pointers, library owned */
+const int32_t* pmf_csr_perm(const pmf_csr* csr);
+const int32_t* pmf_csr_col(const pmf_csr* csr);
+const float* pmf_csr_val(const pmf_csr* csr);
+int64_t pmf_csr_device_bytes(const pmf_csr* csr);
+/* nnz-balanced, row-aligned partition of the rows into `parts` ranges:
+ * h_bounds[parts+1] (host) receives the row boundaries.  Synchronises. */
+int pmf_csr_partition(const pmf_csr* csr, int32_t parts, int32_t* h_bounds);
+
+/* ---- a3/a4: Gamma-Poisson row pass (Poisson MF and HPF-CAVI) ------------------------
+ * Replaces the per-row loops poisson_mf_cavi.py:135-164 / :173-194 (+ E=a/b :167,:197) and
+ * hpf_cavi.py:126-151 / :162-185 (+ :153, :158-159, :187, :192-193).  For every row r of `csr`
+ * (global row R = row_offset + r), with observations t in original order:
+ *     rate_t = max(<E_self[R], E_oth[col_t]>, 1e-10)
+ *     shp[R] = shape_prior + E_self[R] * sum_t (val_t / rate_t) * E_oth[col_t]
+ *     rte[R] = rate_prior(R) + sum_t E_oth[col_t]         rate_prior(R) = d_rate_prior_vec ?
+ *     E_self[R] <- shp[R] / rte[R]   (in place; Jacobi: only row R itself reads E_self[R])
+ *                                                          d_rate_prior_vec[R] : rate_prior
+ * Rows without observations get (shape_prior, rate_prior(R)).
+ * HPF hyper update fused when d_hyper_rate != NULL (hpf_cavi.py:158, :192):
+ *     d_hyper_rate[R] = hyper_rate_prior + sum_k E_self[R,k];  d_hyper_mean[R] = hyper_shape / that
+ * d_hyper_mean may alias d_rate_prior_vec (the user pass reads old E_xi, writes new E_xi).
+ * d_shp / d_rte may be NULL to skip materialising the Gamma parameters.
+ * No per-observation tensor is written: allocations live in registers only.
+ * d_workspace: pmf_gamma_pass_workspace_bytes() bytes of device scratch (partial sums of rows
+ * cut into several segments).
+ */
+int64_t pmf_gamma_pass_workspace_bytes(const pmf_csr* csr, int32_t ld);
+int pmf_gamma_pass(const pmf_csr* csr, int32_t K, int32_t ld,
+                   const float* d_E_oth, float* d_E_self, float* d_shp, float* d_rte,
+                   float shape_prior, float rate_prior, const float* d_rate_prior_vec,
+                   float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior,
+                   void* d_workspace, void* stream);
+
+/* ---- a8-a10: predict and evaluation -------------------------------------------------
+ * predict (poisson_mf_cavi.py:221-241, hpf_cavi.py:215-231, gaussian_mf_cavi_bias.py:291-316,
+ * hpf_pytorch.py:66-69,186-195): pred = <F_user[u], F_item[i]> (+ b_user[u] + b_item[i]) for
+ * u < n_users and i < n_items, else 0; then + global_mean.  d_b_user/d_b_item may be NULL.
+ * softplus != 0 applies torch's softplus (threshold 20) to both rows first (HPF_PyTorch).
+ * d_pred is float64[n] (the dot product is accumulated in float64).
+ */
+int pmf_predict(const int32_t* d_users, const int32_t* d_items, int64_t n,
+                const float* d_F_user, int32_t n_users, const float* d_F_item, int32_t n_items,
+                int32_t K, int32_t ld, const float* d_b_user, const float* d_b_item,
+                float global_mean, int32_t softplus, double* d_pred, void* stream);
+/* Fused predict + error statistics (evaluate_rmse / evaluate_macro_mae, metrics.py:6-16,37-51,
+ * PoissonLogPredictiveLikelihood metrics.py:53-66).  d_label[n] holds each row's index among
+ * the distinct true values (0..n_labels-1, n_labels <= 64).  drop_invalid != 0 skips rows with
+ * unseen ids (Gaussian, gaussian_mf_cavi_bias.py:323-324); otherwise they predict 0 and count.
+ * d_out (float64, zeroed by the call) layout:
+ *   [0] count  [1] sum (y-p)^2  [2] sum |y-p|  [3] sum y*log(max(p,1e-10)) - p - lgamma(y+1)
+ *   [4 .. 4+n_labels) per-label sum |y-p|   [4+n_labels .. 4+2 n_labels) per-label count
+ * (global_mean shifts y_true and the prediction alike, so it cancels in every statistic but [3].) */
+int pmf_eval_stats(const int32_t* d_users, const int32_t* d_items, const float* d_y,
+                   const int32_t* d_label, int32_t n_labels, int64_t n,
+                   const float* d_F_user, int32_t n_users, const float* d_F_item, int32_t n_items,
+                   int32_t K, int32_t ld, const float* d_b_user, const float* d_b_item,
+                   float global_mean, int32_t drop_invalid, double* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMF_B200_H */

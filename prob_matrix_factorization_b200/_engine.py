@@ -1,0 +1,212 @@
+"""Device-side state and sweep loops behind the drop-in model classes.
+
+Python here is host orchestration only: every numeric step on the training path is a
+libpmf_b200 kernel launched through ctypes on torch-owned device memory.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .parallel import RowExchange
+from .ratings import DeviceRatings, as_id_array, to_device
+
+MAX_DEVICE_LABELS = 64
+
+
+def row_stride(K):
+    return _cabi.load().pmf_row_stride(int(K))
+
+
+def pad_table(host, ld, device, pinned=False):
+    """float64/32 (R, K) host array -> float32 (R, ld) CUDA tensor, zero padded."""
+    host = np.asarray(host)
+    R, K = host.shape
+    buf = torch.zeros((R, ld), dtype=torch.float32, pin_memory=pinned)
+    buf[:, :K] = torch.from_numpy(np.ascontiguousarray(host, dtype=np.float32))
+    return buf.to(device, non_blocking=True)
+
+
+def table_to_host(t, K, dtype=np.float64):
+    return t[:, :K].to(torch.float64 if dtype == np.float64 else torch.float32).cpu().numpy()
+
+
+def normalise_ids(ids, n):
+    """Reference predict() uses NumPy fancy indexing: negative ids wrap around once."""
+    ids = np.asarray(ids)
+    if ids.dtype.kind not in "iu":
+        ids = ids.astype(np.int64)
+    ids = ids.astype(np.int64, copy=True)
+    neg = ids < 0
+    if neg.any():
+        ids[neg] += n
+        if (ids < 0).any():
+            raise IndexError("index out of bounds")
+    return np.minimum(ids, np.iinfo(np.int32).max).astype(np.int32)
+
+
+class EvalSet:
+    """A (u, i, rating) frame staged on the device for repeated evaluation."""
+
+    def __init__(self, users, items, y, n_users, n_items, device, drop_invalid=False):
+        users = np.asarray(users)
+        items = np.asarray(items)
+        y = np.asarray(y, dtype=np.float64)
+        self.n = len(y)
+        self.drop_invalid = bool(drop_invalid)
+        u32, i32 = normalise_ids(users, n_users), normalise_ids(items, n_items)
+        y_for_labels = y
+        if drop_invalid:  # gaussian_mf_cavi_bias.py:323-324 filters before np.unique sees the labels
+            ok = (u32 < n_users) & (i32 < n_items)
+            y_for_labels = y[ok]
+        labels = np.unique(y_for_labels)
+        self.labels = labels
+        self.on_device = 0 < len(labels) <= MAX_DEVICE_LABELS
+        self.y_host = y
+        self.u = to_device(u32, device)
+        self.i = to_device(i32, device)
+        self.y = to_device(y.astype(np.float32), device)
+        if self.on_device:
+            lab = np.searchsorted(labels, y).astype(np.int32)
+            lab[(lab >= len(labels)) | (labels[np.minimum(lab, len(labels) - 1)] != y)] = -1
+            self.label = to_device(lab, device)
+            self.n_labels = len(labels)
+        else:
+            self.label, self.n_labels = None, 0
+        self.out = torch.zeros(4 + 2 * MAX_DEVICE_LABELS, dtype=torch.float64, device=device)
+
+
+def eval_stats(ev, F_user, F_item, n_users, n_items, K, ld, b_user=None, b_item=None, global_mean=0.0):
+    """RMSE / macro-MAE / MAE / Poisson LPL of one EvalSet: one fused kernel + one tiny D2H."""
+    with torch.cuda.device(F_user.device):
+        _cabi.call("pmf_eval_stats", ev.u.data_ptr(), ev.i.data_ptr(), ev.y.data_ptr(), _cabi.ptr(ev.label),
+                   ev.n_labels, ev.n, F_user.data_ptr(), n_users, F_item.data_ptr(), n_items, K, ld,
+                   _cabi.ptr(b_user), _cabi.ptr(b_item), float(global_mean), int(ev.drop_invalid),
+                   ev.out.data_ptr(), _cabi.stream_ptr())
+        out = ev.out.cpu().numpy()
+    cnt = out[0]
+    res = {"count": cnt, "rmse": float(np.sqrt(out[1] / cnt)) if cnt > 0 else float("nan"),
+           "mae": float(out[2] / cnt) if cnt > 0 else float("nan"), "poisson_lpl": float(out[3])}
+    if ev.on_device:
+        sae, c = out[4:4 + ev.n_labels], out[4 + ev.n_labels:4 + 2 * ev.n_labels]
+        res["macro_mae"] = float(np.mean(sae[c > 0] / c[c > 0])) if (c > 0).any() else float("nan")
+    else:
+        # more distinct true values than the fused kernel tracks: reduce predictions per label on host
+        pred = predict(ev.u, ev.i, F_user, F_item, n_users, n_items, K, ld, b_user, b_item, global_mean)
+        y = ev.y_host + global_mean
+        if ev.drop_invalid:
+            ok = ((ev.u < n_users) & (ev.i < n_items)).cpu().numpy()
+            y, pred = y[ok], pred[ok]
+        per = [np.mean(np.abs(y[y == lab] - pred[y == lab])) for lab in np.unique(y)]
+        res["macro_mae"] = float(np.mean(per)) if per else float("nan")
+    return res
+
+
+def predict(u_dev, i_dev, F_user, F_item, n_users, n_items, K, ld, b_user=None, b_item=None, global_mean=0.0,
+            softplus=False):
+    """Device ids -> float64 NumPy predictions (pmf_predict)."""
+    n = u_dev.numel()
+    out = torch.empty(n, dtype=torch.float64, device=F_user.device)
+    with torch.cuda.device(F_user.device):
+        _cabi.call("pmf_predict", u_dev.data_ptr(), i_dev.data_ptr(), n, F_user.data_ptr(), n_users,
+                   F_item.data_ptr(), n_items, K, ld, _cabi.ptr(b_user), _cabi.ptr(b_item), float(global_mean),
+                   int(bool(softplus)), out.data_ptr(), _cabi.stream_ptr())
+    return out.cpu().numpy()
+
+
+class GammaEngine:
+    """Poisson MF / HPF-CAVI state on one GPU (one shard of the ratings) and its sweep.
+
+    Sweep order follows SURVEY.md Appendix A: user pass (old E_theta, E_beta[, E_xi]) -> E_theta
+    [-> xi] -> item pass (NEW E_theta, old E_beta[, E_eta]) -> E_beta [-> eta]; two dependent
+    SDDMM+reduce passes per iteration.
+    """
+
+    def __init__(self, ratings: DeviceRatings, K, user_shape, item_shape, user_rate=None, item_rate=None,
+                 hyper=None, keep_params=True):
+        self.r = ratings
+        self.dev = ratings.device
+        self.K = int(K)
+        self.ld = row_stride(K)
+        self.N, self.M = ratings.n_users, ratings.n_items
+        self.user_shape, self.item_shape = float(user_shape), float(item_shape)
+        self.user_rate = None if user_rate is None else float(user_rate)
+        self.item_rate = None if item_rate is None else float(item_rate)
+        # hyper = dict(user_shape=a_xi, user_rate_prior=b', item_shape=a_eta, item_rate_prior=d') for HPF
+        self.hyper = hyper
+        self.keep_params = keep_params
+        f = lambda rows: torch.zeros((rows, self.ld), dtype=torch.float32, device=self.dev)
+        self.E_theta, self.E_beta = f(self.N), f(self.M)
+        self.shp_theta = f(self.N) if keep_params else None
+        self.rte_theta = f(self.N) if keep_params else None
+        self.shp_beta = f(self.M) if keep_params else None
+        self.rte_beta = f(self.M) if keep_params else None
+        if hyper is not None:
+            v = lambda rows: torch.zeros(rows, dtype=torch.float32, device=self.dev)
+            self.rate_xi, self.E_xi, self.rate_eta, self.E_eta = v(self.N), v(self.N), v(self.M), v(self.M)
+        else:
+            self.rate_xi = self.E_xi = self.rate_eta = self.E_eta = None
+        self.ws_user = ratings.by_user.workspace(self.ld) if ratings.by_user is not None else None
+        self.ws_item = ratings.by_item.workspace(self.ld) if ratings.by_item is not None else None
+        self.xu = RowExchange(ratings.user_bounds) if ratings.world > 1 else None
+        self.xi_ = RowExchange(ratings.item_bounds) if ratings.world > 1 else None
+        self.launches_per_sweep = sum(
+            (1 if g.n_segments > 0 else 0) + (1 if g.n_multi_rows > 0 else 0)
+            for g in (ratings.by_user, ratings.by_item) if g is not None)
+
+    # -- state upload --------------------------------------------------------------------------
+    def load_means(self, E_theta, E_beta, E_xi=None, E_eta=None):
+        """Upload the initial expectations (host float64, drawn by NumPy exactly as the reference)."""
+        self.E_theta.copy_(pad_table(E_theta, self.ld, self.dev))
+        self.E_beta.copy_(pad_table(E_beta, self.ld, self.dev))
+        if self.hyper is not None:
+            self.E_xi.copy_(to_device(np.asarray(E_xi, dtype=np.float32), self.dev))
+            self.E_eta.copy_(to_device(np.asarray(E_eta, dtype=np.float32), self.dev))
+
+    # -- one pass ------------------------------------------------------------------------------
+    def _pass(self, grouped, E_oth, E_self, shp, rte, shape_prior, rate_prior, rate_vec, hyper_rate, hyper_mean,
+              hyper_shape, hyper_rate_prior, ws):
+        if grouped is None:
+            return
+        _cabi.call("pmf_gamma_pass", grouped.handle, self.K, self.ld, E_oth.data_ptr(), E_self.data_ptr(),
+                   _cabi.ptr(shp), _cabi.ptr(rte), shape_prior, 0.0 if rate_prior is None else rate_prior,
+                   _cabi.ptr(rate_vec), _cabi.ptr(hyper_rate), _cabi.ptr(hyper_mean), hyper_shape,
+                   hyper_rate_prior, _cabi.ptr(ws), _cabi.stream_ptr())
+
+    def user_pass(self):
+        h = self.hyper
+        self._pass(self.r.by_user, self.E_beta, self.E_theta, self.shp_theta, self.rte_theta, self.user_shape,
+                   self.user_rate, self.E_xi, self.rate_xi, self.E_xi,
+                   h["user_shape"] if h else 0.0, h["user_rate_prior"] if h else 0.0, self.ws_user)
+        if self.xu is not None:
+            self.xu.gather(*([self.E_theta] + ([self.E_xi] if h else [])))
+
+    def item_pass(self):
+        h = self.hyper
+        self._pass(self.r.by_item, self.E_theta, self.E_beta, self.shp_beta, self.rte_beta, self.item_shape,
+                   self.item_rate, self.E_eta, self.rate_eta, self.E_eta,
+                   h["item_shape"] if h else 0.0, h["item_rate_prior"] if h else 0.0, self.ws_item)
+        if self.xi_ is not None:
+            self.xi_.gather(*([self.E_beta] + ([self.E_eta] if h else [])))
+
+    def sweep(self):
+        with torch.cuda.device(self.dev):
+            self.user_pass()
+            self.item_pass()
+
+    def sync_params(self):
+        """Multi-GPU: make the Gamma shape/rate tables (only needed as outputs) complete on every rank."""
+        if self.xu is None or not self.keep_params:
+            return
+        self.xu.gather(*([self.shp_theta, self.rte_theta] + ([self.rate_xi] if self.hyper else [])))
+        self.xi_.gather(*([self.shp_beta, self.rte_beta] + ([self.rate_eta] if self.hyper else [])))
+
+    # -- accounting ----------------------------------------------------------------------------
+    def algorithmic_bytes_per_sweep(self):
+        """per pass nnz*(4K+8) + R*(16K+4) (+12 R for the HPF hyper vectors)."""
+        K, nnz = self.K, self.r.nnz
+        per_row = 16 * K + 4 + (12 if self.hyper is not None else 0)
+        return 2 * nnz * (4 * K + 8) + (self.N + self.M) * per_row

@@ -1,0 +1,524 @@
+// a1: observation grouping on the device -- stable LSD radix sort + row pointers + the
+// segment decomposition consumed by the pass kernels.
+//
+// Replaces the reference's _build_index_lists (poisson_mf_cavi.py:73-84 and its copies): a
+// Python loop that appends observation t to the list of row key[t].  The result is the stable
+// sort of arange(nnz) by key, which is what the radix sort below produces bit for bit.
+//
+// HBM-bound integer work: every pass streams (key, index) pairs once in and once out; ranks
+// are computed with warp match + shared-memory counters, no global atomics.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace pmf {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------
+// exclusive scan (int32), hierarchical: 4096 items per block
+// ------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                                 int64_t n, int32_t* __restrict__ tile_sums) {
+    __shared__ int32_t warp_tot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int32_t v[kScanItems];
+    int32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        sum += v[k];
+    }
+    int32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int32_t w = warp_tot[lane];
+        int32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        warp_tot[lane] = wi - w;  // exclusive over warps
+        if (lane == 31 && tile_sums) tile_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    int32_t run = warp_tot[warp] + incl - sum;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
+
+__global__ void scan_add_kernel(int32_t* __restrict__ out, int64_t n, const int32_t* __restrict__ tile_offsets) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += tile_offsets[i / kScanTile];
+}
+
+__global__ void scan_total_kernel(const int32_t* __restrict__ excl, const int32_t* __restrict__ last_in,
+                                  int32_t* __restrict__ total) {
+    *total = *excl + *last_in;
+}
+
+int exclusive_scan_i32(const int32_t* d_in, int32_t* d_out, int64_t n, int32_t* d_total, cudaStream_t s) {
+    if (n <= 0) {
+        if (d_total) PMF_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int32_t), s));
+        return PMF_OK;
+    }
+    // the total needs the last input element, which an in-place scan overwrites: save it first
+    int32_t* d_last = nullptr;
+    if (d_total) {
+        PMF_TRY(alloc_async(&d_last, 1, s));
+        PMF_CUDA(cudaMemcpyAsync(d_last, d_in + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    }
+    const int64_t tiles = cdiv(n, kScanTile);
+    int32_t* d_sums = nullptr;
+    if (tiles > 1) PMF_TRY(alloc_async(&d_sums, tiles, s));
+    scan_tile_kernel<<<(unsigned)tiles, kScanThreads, 0, s>>>(d_in, d_out, n, d_sums);
+    PMF_LAUNCH_CHECK();
+    if (tiles > 1) {
+        PMF_TRY(exclusive_scan_i32(d_sums, d_sums, tiles, nullptr, s));
+        scan_add_kernel<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(d_out, n, d_sums);
+        PMF_LAUNCH_CHECK();
+        free_async(d_sums, s);
+    }
+    if (d_total) {
+        scan_total_kernel<<<1, 1, 0, s>>>(d_out + (n - 1), d_last, d_total);
+        PMF_LAUNCH_CHECK();
+        free_async(d_last, s);
+    }
+    return PMF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stable LSD radix sort of (key, original index), 8-bit digits, 4096-item tiles
+// ------------------------------------------------------------------------------------------
+constexpr int kSortThreads = 256;
+constexpr int kSortRounds = 16;                       // items per thread
+constexpr int kSortTile = kSortThreads * kSortRounds;  // 4096
+constexpr int kWarpChunk = 32 * kSortRounds;           // each warp ranks a contiguous 512-item chunk
+
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const int32_t* __restrict__ keys, int64_t n, int shift,
+                                                                  int32_t* __restrict__ hist, int n_tiles) {
+    __shared__ int32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        const int64_t idx = base + r * kSortThreads + threadIdx.x;
+        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255], 1);
+    }
+    __syncthreads();
+    hist[(int64_t)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];  // digit-major
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const int32_t* __restrict__ keys_in,
+                                                                     const int32_t* __restrict__ vals_in,
+                                                                     int32_t* __restrict__ keys_out,
+                                                                     int32_t* __restrict__ vals_out, int64_t n, int shift,
+                                                                     const int32_t* __restrict__ offsets, int n_tiles) {
+    __shared__ int32_t cnt[kSortThreads / 32][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int d = threadIdx.x; d < (kSortThreads / 32) * 256; d += kSortThreads) (&cnt[0][0])[d] = 0;
+    __syncthreads();
+    const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)warp * kWarpChunk;
+    int32_t key[kSortRounds], val[kSortRounds], rank[kSortRounds];
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        const int64_t idx = wbase + r * 32 + lane;
+        const bool ok = idx < n;
+        key[r] = ok ? keys_in[idx] : 0;
+        val[r] = FIRST ? (int32_t)idx : (ok ? vals_in[idx] : 0);
+    }
+    // rank inside this warp's chunk, in input order (round-major, then lane): stable
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        const bool ok = (wbase + r * 32 + lane) < n;
+        const int d = ok ? ((key[r] >> shift) & 255) : (256 + lane);  // inactive lanes match nobody
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int below = __popc(peers & ((1u << lane) - 1u));
+        const int old = ok ? cnt[warp][d] : 0;
+        __syncwarp();
+        if (ok && below == 0) cnt[warp][d] = old + __popc(peers);
+        __syncwarp();
+        rank[r] = old + below;
+    }
+    __syncthreads();
+    {   // digit d: global offset of (digit, tile) then exclusive prefix over the tile's warps
+        const int d = threadIdx.x;
+        int32_t run = offsets[(int64_t)d * n_tiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < kSortThreads / 32; ++w) {
+            const int32_t t = cnt[w][d];
+            cnt[w][d] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        if ((wbase + r * 32 + lane) < n) {
+            const int32_t pos = cnt[warp][(key[r] >> shift) & 255] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
+    }
+}
+
+// row_ptr from sorted keys: the thread at position p closes every row in (key[p-1], key[p]]
+__global__ void row_ptr_kernel(const int32_t* __restrict__ sorted_keys, int64_t n, int32_t n_rows,
+                               int32_t* __restrict__ row_ptr) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int32_t k = sorted_keys[p];
+    const int32_t kp = (p == 0) ? -1 : sorted_keys[p - 1];
+    for (int32_t r = kp + 1; r <= k; ++r) row_ptr[r] = (int32_t)p;
+    if (p == n - 1)
+        for (int32_t r = k + 1; r <= n_rows; ++r) row_ptr[r] = (int32_t)n;
+}
+
+__global__ void gather_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ other,
+                              const float* __restrict__ x, int64_t n, int32_t* __restrict__ col, float* __restrict__ val) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int32_t t = perm[p];
+    col[p] = other[t];
+    val[p] = x[t];
+}
+
+__global__ void check_keys_kernel(const int32_t* __restrict__ key, const int32_t* __restrict__ other, int64_t n,
+                                  int32_t n_rows, int32_t* __restrict__ bad) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    if (key[p] < 0 || key[p] >= n_rows || other[p] < 0) atomicOr(bad, 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// segment decomposition
+// ------------------------------------------------------------------------------------------
+__global__ void seg_count_kernel(const int32_t* __restrict__ row_ptr, int32_t n_rows, int32_t seg_len,
+                                 int32_t* __restrict__ seg_cnt, int32_t* __restrict__ multi_flag,
+                                 int32_t* __restrict__ part_cnt) {
+    const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int32_t len = row_ptr[r + 1] - row_ptr[r];
+    const int32_t ns = len <= seg_len ? 1 : (len + seg_len - 1) / seg_len;
+    seg_cnt[r] = ns;
+    multi_flag[r] = ns > 1;
+    part_cnt[r] = ns > 1 ? ns : 0;
+}
+
+__global__ void seg_fill_kernel(const int32_t* __restrict__ row_ptr, int32_t n_rows, int32_t seg_len,
+                                const int32_t* __restrict__ seg_off, const int32_t* __restrict__ multi_off,
+                                const int32_t* __restrict__ part_off, int32_t n_multi, int32_t n_partial,
+                                int32_t* __restrict__ seg_row, int32_t* __restrict__ seg_start,
+                                int32_t* __restrict__ seg_partial, int32_t* __restrict__ multi_row,
+                                int32_t* __restrict__ multi_first) {
+    const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) multi_first[n_multi] = n_partial;
+    if (r >= n_rows) return;
+    const int32_t b = row_ptr[r], e = row_ptr[r + 1];
+    const int32_t len = e - b;
+    const int32_t ns = len <= seg_len ? 1 : (len + seg_len - 1) / seg_len;
+    const int32_t s0 = seg_off[r];
+    if (ns == 1) {
+        seg_row[s0] = r;
+        seg_start[s0] = b;
+        seg_partial[s0] = -1;
+        return;
+    }
+    const int32_t p0 = part_off[r];
+    multi_row[multi_off[r]] = r;
+    multi_first[multi_off[r]] = p0;
+    for (int32_t j = 0; j < ns; ++j) {
+        seg_row[s0 + j] = r;
+        seg_start[s0 + j] = b + j * seg_len;
+        seg_partial[s0 + j] = p0 + j;
+    }
+}
+
+__global__ void rebase_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int32_t n, int32_t base) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] - base;
+}
+
+}  // namespace pmf
+
+using namespace pmf;
+
+struct pmf_csr {
+    int64_t nnz = 0;
+    int32_t n_rows = 0, row_offset = 0, seg_len = 0;
+    int32_t n_seg = 0, n_multi = 0, n_partial = 0;
+    int32_t *row_ptr = nullptr, *perm = nullptr, *col = nullptr;
+    float* val = nullptr;
+    int32_t *seg_row = nullptr, *seg_start = nullptr, *seg_partial = nullptr;
+    int32_t *multi_row = nullptr, *multi_first = nullptr;
+    int64_t bytes = 0;
+};
+
+static int dev_alloc(void** p, int64_t bytes, pmf_csr* c) {
+    if (bytes <= 0) bytes = 4;
+    cudaError_t e = cudaMalloc(p, (size_t)bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%lld bytes) failed: %s", (long long)bytes, cudaGetErrorString(e));
+        return PMF_ENOMEM;
+    }
+    c->bytes += bytes;
+    return PMF_OK;
+}
+
+// Builds seg_* / multi_* for c (row_ptr must be final).  Synchronises the stream.
+static int build_segments(pmf_csr* c, cudaStream_t s) {
+    const int32_t R = c->n_rows;
+    int32_t *seg_cnt = nullptr, *multi_flag = nullptr, *part_cnt = nullptr, *totals = nullptr;
+    PMF_TRY(alloc_async(&seg_cnt, R, s));
+    PMF_TRY(alloc_async(&multi_flag, R, s));
+    PMF_TRY(alloc_async(&part_cnt, R, s));
+    PMF_TRY(alloc_async(&totals, 3, s));
+    const unsigned grid = (unsigned)cdiv(R > 0 ? R : 1, 256);
+    seg_count_kernel<<<grid, 256, 0, s>>>(c->row_ptr, R, c->seg_len, seg_cnt, multi_flag, part_cnt);
+    PMF_LAUNCH_CHECK();
+    PMF_TRY(exclusive_scan_i32(seg_cnt, seg_cnt, R, totals + 0, s));
+    PMF_TRY(exclusive_scan_i32(multi_flag, multi_flag, R, totals + 1, s));
+    PMF_TRY(exclusive_scan_i32(part_cnt, part_cnt, R, totals + 2, s));
+    int32_t h_tot[3] = {0, 0, 0};
+    PMF_CUDA(cudaMemcpyAsync(h_tot, totals, sizeof(h_tot), cudaMemcpyDeviceToHost, s));
+    PMF_CUDA(cudaStreamSynchronize(s));
+    c->n_seg = h_tot[0];
+    c->n_multi = h_tot[1];
+    c->n_partial = h_tot[2];
+    PMF_TRY(dev_alloc((void**)&c->seg_row, (int64_t)c->n_seg * 4, c));
+    PMF_TRY(dev_alloc((void**)&c->seg_start, (int64_t)c->n_seg * 4, c));
+    PMF_TRY(dev_alloc((void**)&c->seg_partial, (int64_t)c->n_seg * 4, c));
+    PMF_TRY(dev_alloc((void**)&c->multi_row, (int64_t)c->n_multi * 4, c));
+    PMF_TRY(dev_alloc((void**)&c->multi_first, ((int64_t)c->n_multi + 1) * 4, c));
+    seg_fill_kernel<<<grid, 256, 0, s>>>(c->row_ptr, R, c->seg_len, seg_cnt, multi_flag, part_cnt, c->n_multi,
+                                         c->n_partial, c->seg_row, c->seg_start, c->seg_partial, c->multi_row,
+                                         c->multi_first);
+    PMF_LAUNCH_CHECK();
+    free_async(seg_cnt, s);
+    free_async(multi_flag, s);
+    free_async(part_cnt, s);
+    free_async(totals, s);
+    PMF_CUDA(cudaStreamSynchronize(s));
+    return PMF_OK;
+}
+
+extern "C" {
+
+int pmf_version(void) { return 100; }
+const char* pmf_last_error(void) { return g_err; }
+
+int pmf_device_count(int* count) {
+    PMF_REQUIRE(count != nullptr, "count is NULL");
+    PMF_CUDA(cudaGetDeviceCount(count));
+    return PMF_OK;
+}
+
+int pmf_copy_to_host(void* h_dst, const void* d_src, int64_t bytes, void* stream) {
+    PMF_REQUIRE(bytes >= 0 && (bytes == 0 || (h_dst && d_src)), "bad argument");
+    if (bytes == 0) return PMF_OK;
+    PMF_CUDA(cudaMemcpyAsync(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PMF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return PMF_OK;
+}
+
+int pmf_row_stride(int K) { return K <= 0 ? 0 : ((K + 7) / 8) * 8; }
+
+int pmf_csr_free(pmf_csr* c) {
+    if (!c) return PMF_OK;
+    void* ptrs[] = {c->row_ptr, c->perm, c->col, c->val, c->seg_row, c->seg_start, c->seg_partial, c->multi_row,
+                    c->multi_first};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete c;
+    return PMF_OK;
+}
+
+int pmf_csr_build(const int32_t* d_key, const int32_t* d_other, const float* d_val, int64_t nnz, int32_t n_rows,
+                  int32_t seg_len, void* stream, pmf_csr** out) {
+    PMF_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    PMF_REQUIRE(nnz >= 0 && nnz < (int64_t)INT32_MAX, "nnz=%lld out of range", (long long)nnz);
+    PMF_REQUIRE(n_rows > 0, "n_rows=%d must be positive", n_rows);
+    PMF_REQUIRE(seg_len >= 8 && seg_len % 8 == 0, "seg_len=%d must be a positive multiple of 8", seg_len);
+    PMF_REQUIRE(nnz == 0 || (d_key && d_other && d_val), "NULL input with nnz > 0");
+    cudaStream_t s = (cudaStream_t)stream;
+    pmf_csr* c = new pmf_csr();
+    c->nnz = nnz;
+    c->n_rows = n_rows;
+    c->seg_len = seg_len;
+    int st = PMF_OK;
+    auto fail = [&](int code) {
+        pmf_csr_free(c);
+        return code;
+    };
+    if ((st = dev_alloc((void**)&c->row_ptr, ((int64_t)n_rows + 1) * 4, c)) != PMF_OK) return fail(st);
+    if ((st = dev_alloc((void**)&c->perm, nnz * 4, c)) != PMF_OK) return fail(st);
+    if ((st = dev_alloc((void**)&c->col, nnz * 4, c)) != PMF_OK) return fail(st);
+    if ((st = dev_alloc((void**)&c->val, nnz * 4, c)) != PMF_OK) return fail(st);
+
+    if (nnz == 0) {
+        if (cudaMemsetAsync(c->row_ptr, 0, ((size_t)n_rows + 1) * 4, s) != cudaSuccess) return fail(PMF_ECUDA);
+    } else {
+        auto body = [&]() -> int {
+            int32_t* bad = nullptr;
+            PMF_TRY(alloc_async(&bad, 1, s));
+            PMF_CUDA(cudaMemsetAsync(bad, 0, 4, s));
+            check_keys_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(d_key, d_other, nnz, n_rows, bad);
+            PMF_LAUNCH_CHECK();
+            int32_t h_bad = 0;
+            PMF_CUDA(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, s));
+            PMF_CUDA(cudaStreamSynchronize(s));
+            free_async(bad, s);
+            PMF_REQUIRE(h_bad == 0, "ids out of range: keys must lie in [0, %d), other ids must be >= 0", n_rows);
+
+            int bits = 1;
+            while (bits < 31 && (1ll << bits) < (int64_t)n_rows) ++bits;
+            const int passes = (bits + 7) / 8;
+            const int n_tiles = (int)cdiv(nnz, kSortTile);
+            int32_t *k0 = nullptr, *k1 = nullptr, *v1 = nullptr, *hist = nullptr;
+            PMF_TRY(alloc_async(&k0, nnz, s));
+            PMF_TRY(alloc_async(&hist, (int64_t)256 * n_tiles, s));
+            if (passes > 1) {
+                PMF_TRY(alloc_async(&k1, nnz, s));
+                PMF_TRY(alloc_async(&v1, nnz, s));
+            }
+            // ping-pong so that the LAST pass lands in (k0, c->perm)
+            const int32_t* kin = d_key;
+            const int32_t* vin = nullptr;
+            for (int p = 0; p < passes; ++p) {
+                const bool to_final = ((passes - 1 - p) % 2) == 0;
+                int32_t* kout = to_final ? k0 : k1;
+                int32_t* vout = to_final ? c->perm : v1;
+                radix_hist_kernel<<<n_tiles, kSortThreads, 0, s>>>(kin, nnz, 8 * p, hist, n_tiles);
+                PMF_LAUNCH_CHECK();
+                PMF_TRY(exclusive_scan_i32(hist, hist, (int64_t)256 * n_tiles, nullptr, s));
+                if (p == 0)
+                    radix_scatter_kernel<true><<<n_tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, nnz, 8 * p, hist, n_tiles);
+                else
+                    radix_scatter_kernel<false><<<n_tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, nnz, 8 * p, hist, n_tiles);
+                PMF_LAUNCH_CHECK();
+                kin = kout;
+                vin = vout;
+            }
+            row_ptr_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(k0, nnz, n_rows, c->row_ptr);
+            PMF_LAUNCH_CHECK();
+            gather_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(c->perm, d_other, d_val, nnz, c->col, c->val);
+            PMF_LAUNCH_CHECK();
+            free_async(k0, s);
+            free_async(k1, s);
+            free_async(v1, s);
+            free_async(hist, s);
+            return PMF_OK;
+        };
+        if ((st = body()) != PMF_OK) return fail(st);
+    }
+    if ((st = build_segments(c, s)) != PMF_OK) return fail(st);
+    *out = c;
+    return PMF_OK;
+}
+
+int pmf_csr_slice(const pmf_csr* src, int32_t row_begin, int32_t row_end, void* stream, pmf_csr** out) {
+    PMF_REQUIRE(src && out, "NULL argument");
+    *out = nullptr;
+    PMF_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= src->n_rows, "bad row range [%d,%d) of %d",
+                row_begin, row_end, src->n_rows);
+    PMF_REQUIRE(row_end > row_begin, "empty row range");
+    cudaStream_t s = (cudaStream_t)stream;
+    int32_t h_b = 0, h_e = 0;
+    PMF_CUDA(cudaMemcpyAsync(&h_b, src->row_ptr + row_begin, 4, cudaMemcpyDeviceToHost, s));
+    PMF_CUDA(cudaMemcpyAsync(&h_e, src->row_ptr + row_end, 4, cudaMemcpyDeviceToHost, s));
+    PMF_CUDA(cudaStreamSynchronize(s));
+    pmf_csr* c = new pmf_csr();
+    c->nnz = h_e - h_b;
+    c->n_rows = row_end - row_begin;
+    c->row_offset = src->row_offset + row_begin;
+    c->seg_len = src->seg_len;
+    auto body = [&]() -> int {
+        PMF_TRY(dev_alloc((void**)&c->row_ptr, ((int64_t)c->n_rows + 1) * 4, c));
+        PMF_TRY(dev_alloc((void**)&c->perm, c->nnz * 4, c));
+        PMF_TRY(dev_alloc((void**)&c->col, c->nnz * 4, c));
+        PMF_TRY(dev_alloc((void**)&c->val, c->nnz * 4, c));
+        rebase_kernel<<<(unsigned)cdiv(c->n_rows + 1, 256), 256, 0, s>>>(src->row_ptr + row_begin, c->row_ptr,
+                                                                         c->n_rows + 1, h_b);
+        PMF_LAUNCH_CHECK();
+        if (c->nnz > 0) {
+            PMF_CUDA(cudaMemcpyAsync(c->perm, src->perm + h_b, c->nnz * 4, cudaMemcpyDeviceToDevice, s));
+            PMF_CUDA(cudaMemcpyAsync(c->col, src->col + h_b, c->nnz * 4, cudaMemcpyDeviceToDevice, s));
+            PMF_CUDA(cudaMemcpyAsync(c->val, src->val + h_b, c->nnz * 4, cudaMemcpyDeviceToDevice, s));
+        }
+        return build_segments(c, s);
+    };
+    int st = body();
+    if (st != PMF_OK) {
+        pmf_csr_free(c);
+        return st;
+    }
+    *out = c;
+    return PMF_OK;
+}
+
+int64_t pmf_csr_nnz(const pmf_csr* c) { return c ? c->nnz : -1; }
+int32_t pmf_csr_rows(const pmf_csr* c) { return c ? c->n_rows : -1; }
+int32_t pmf_csr_row_offset(const pmf_csr* c) { return c ? c->row_offset : -1; }
+int32_t pmf_csr_segments(const pmf_csr* c) { return c ? c->n_seg : -1; }
+int32_t pmf_csr_multi_rows(const pmf_csr* c) { return c ? c->n_multi : -1; }
+int32_t pmf_csr_seg_len(const pmf_csr* c) { return c ? c->seg_len : -1; }
+const int32_t* pmf_csr_row_ptr(const pmf_csr* c) { return c ? c->row_ptr : nullptr; }
+const int32_t* pmf_csr_perm(const pmf_csr* c) { return c ? c->perm : nullptr; }
+const int32_t* pmf_csr_col(const pmf_csr* c) { return c ? c->col : nullptr; }
+const float* pmf_csr_val(const pmf_csr* c) { return c ? c->val : nullptr; }
+int64_t pmf_csr_device_bytes(const pmf_csr* c) { return c ? c->bytes : -1; }
+
+int pmf_csr_partition(const pmf_csr* c, int32_t parts, int32_t* h_bounds) {
+    PMF_REQUIRE(c && h_bounds && parts >= 1, "bad argument");
+    std::vector<int32_t> rp((size_t)c->n_rows + 1);
+    PMF_CUDA(cudaMemcpy(rp.data(), c->row_ptr, rp.size() * 4, cudaMemcpyDeviceToHost));
+    h_bounds[0] = 0;
+    for (int32_t p = 1; p < parts; ++p) {
+        const int64_t target = (c->nnz * p) / parts;
+        // first row whose start is >= target, never before the previous boundary
+        int32_t lo = h_bounds[p - 1], hi = c->n_rows;
+        while (lo < hi) {
+            const int32_t mid = lo + (hi - lo) / 2;
+            if ((int64_t)rp[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        h_bounds[p] = lo;
+    }
+    h_bounds[parts] = c->n_rows;
+    return PMF_OK;
+}
+
+}  // extern "C"
+
+// Internal accessors for the other translation units.
+namespace pmf {
+CsrView csr_view(const pmf_csr* c) {
+    return CsrView{c->nnz, c->n_rows, c->row_offset, c->seg_len, c->n_seg, c->n_multi, c->n_partial, c->row_ptr,
+                   c->col, c->val, c->seg_row, c->seg_start, c->seg_partial, c->multi_row, c->multi_first};
+}
+}  // namespace pmf

@@ -1,0 +1,296 @@
+// a3/a4: the fused Gamma-Poisson row pass shared by Poisson MF and HPF-CAVI.
+//
+// Reference loops replaced: poisson_mf_cavi.py:135-164, :173-194 (+ :167, :197) and
+// hpf_cavi.py:126-151, :162-185 (+ :153, :158-159, :187, :192-193).
+//
+// One kernel does, per observed rating, the SDDMM  rate = <E_self[row], E_oth[col]>, the
+// allocation  (x / rate) * E_oth[col] * E_self[row]  and the segmented row sums of the allocation
+// and of E_oth[col]; the Gamma shape/rate update, E = shape/rate and the HPF hyper-rate update run in
+// the same kernel's epilogue.  Nothing per-observation is written to HBM.
+//
+// Mapping: a GROUP of G lanes owns one segment (<= seg_len observations of one row).  Each lane keeps
+// V float4 slices of the K-wide rows in registers (slice index = lane + v*G, so the G lanes of a load
+// instruction read 16*G contiguous bytes).  Per G observations the group reads col/val with one
+// coalesced load per lane and broadcasts them with shuffles; U gathered rows are kept in flight per
+// lane.  The dot product is reduced over the G lanes with log2(G) xor-shuffles.  Rows cut into several
+// segments write their partial sums to a scratch buffer and a second, tiny kernel combines them in
+// segment order (deterministic, no atomics).
+//
+// HBM-bound: 4*ld + 8 bytes per observation, 16*ld + 4 per row.
+#include "common.cuh"
+
+namespace pmf {
+
+struct GammaArgs {
+    const int32_t *seg_row, *seg_start, *seg_partial, *row_ptr, *col;
+    const float* val;
+    const int32_t *multi_row, *multi_first;
+    int32_t n_seg, n_multi, seg_len, row_offset, K, ld, nvec;
+    const float* E_oth;
+    float* E_self;
+    float* shp;
+    float* rte;
+    float shape_prior, rate_prior;
+    const float* rate_prior_vec;
+    float* hyper_rate;
+    float* hyper_mean;
+    float hyper_shape, hyper_rate_prior;
+    float* partial;  // [n_partial][2*ld]: sum (x/rate) E_oth | sum E_oth
+};
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// Sum over the G lanes of a group.  `mask` names the participating lanes: the full warp inside the
+// warp-uniform main loop, only the group's own lanes in the (group-divergent) epilogues.
+template <int G>
+__device__ __forceinline__ float group_sum(float v, unsigned mask = 0xffffffffu) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+
+template <int G>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+    return G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
+}
+
+// Gamma update for global row R from the row's complete sums.  Executed by the G lanes of a group.
+template <int G, int V, bool HYPER>
+__device__ __forceinline__ void gamma_row_update(const GammaArgs& a, int R, int gl, unsigned gmask,
+                                                 const float4 (&self)[V], const float4 (&sa)[V],
+                                                 const float4 (&sb)[V]) {
+    const float rp = a.rate_prior_vec ? a.rate_prior_vec[R] : a.rate_prior;
+    float esum = 0.f;
+    const size_t rowoff = (size_t)R * a.ld;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int idx = gl + v * G;
+        if (idx < a.nvec) {
+            const int k0 = idx * 4;
+            float4 s, r, e;
+            s.x = a.shape_prior + self[v].x * sa[v].x;  r.x = rp + sb[v].x;  e.x = s.x / r.x;
+            s.y = a.shape_prior + self[v].y * sa[v].y;  r.y = rp + sb[v].y;  e.y = s.y / r.y;
+            s.z = a.shape_prior + self[v].z * sa[v].z;  r.z = rp + sb[v].z;  e.z = s.z / r.z;
+            s.w = a.shape_prior + self[v].w * sa[v].w;  r.w = rp + sb[v].w;  e.w = s.w / r.w;
+            // padding columns K..ld-1 stay (shape 0, rate 1, mean 0) so they never reach a dot product
+            if (k0 + 0 >= a.K) { s.x = 0.f; r.x = 1.f; e.x = 0.f; }
+            if (k0 + 1 >= a.K) { s.y = 0.f; r.y = 1.f; e.y = 0.f; }
+            if (k0 + 2 >= a.K) { s.z = 0.f; r.z = 1.f; e.z = 0.f; }
+            if (k0 + 3 >= a.K) { s.w = 0.f; r.w = 1.f; e.w = 0.f; }
+            if (a.shp) *reinterpret_cast<float4*>(a.shp + rowoff + k0) = s;
+            if (a.rte) *reinterpret_cast<float4*>(a.rte + rowoff + k0) = r;
+            *reinterpret_cast<float4*>(a.E_self + rowoff + k0) = e;
+            esum += (e.x + e.y) + (e.z + e.w);
+        }
+    }
+    if (HYPER) {
+        esum = group_sum<G>(esum, gmask);
+        if (gl == 0) {
+            const float hr = a.hyper_rate_prior + esum;   // hpf_cavi.py:158 / :192
+            a.hyper_rate[R] = hr;
+            a.hyper_mean[R] = a.hyper_shape / hr;          // hpf_cavi.py:94-95
+        }
+    }
+}
+
+template <int G, int V, int U, bool HYPER>
+__global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
+    static_assert(G == 4 || G == 8 || G == 16 || G == 32, "group size");
+    static_assert(G % U == 0, "U must divide G");
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool has = gid < a.n_seg;
+    int row = 0, p = 0, end = 0, pidx = -1;
+    if (has) {
+        row = a.seg_row[gid];
+        p = a.seg_start[gid];
+        end = min(p + a.seg_len, a.row_ptr[row + 1]);
+        pidx = a.seg_partial[gid];
+    }
+    const int R = a.row_offset + row;
+    float4 self[V], sa[V], sb[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int idx = gl + v * G;
+        self[v] = (has && idx < a.nvec) ? *reinterpret_cast<const float4*>(a.E_self + (size_t)R * a.ld + idx * 4) : f4_zero();
+        sa[v] = f4_zero();
+        sb[v] = f4_zero();
+    }
+    // warp-uniform trip count so that full-mask shuffles are legal; short groups idle on predicates
+    const int maxlen = __reduce_max_sync(0xffffffffu, end - p);
+    for (int base = 0; base < maxlen; base += G) {
+        const int q = p + base + gl;
+        const bool okq = q < end;
+        const int c_l = okq ? __ldg(a.col + q) : 0;
+        const float x_l = okq ? __ldg(a.val + q) : 0.f;
+        const int rem = end - (p + base);
+#pragma unroll
+        for (int j0 = 0; j0 < G; j0 += U) {
+            float4 o[U][V];
+#pragma unroll
+            for (int jj = 0; jj < U; ++jj) {
+                const int j = j0 + jj;
+                const int c = __shfl_sync(0xffffffffu, c_l, j, G);
+                const float* rowp = a.E_oth + (size_t)c * a.ld;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const int idx = gl + v * G;
+                    o[jj][v] = (j < rem && idx < a.nvec) ? ldg_f4(rowp + idx * 4) : f4_zero();
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < U; ++jj) {
+                const int j = j0 + jj;
+                const float x = __shfl_sync(0xffffffffu, x_l, j, G);
+                float d = 0.f;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    d = fmaf(self[v].x, o[jj][v].x, d);
+                    d = fmaf(self[v].y, o[jj][v].y, d);
+                    d = fmaf(self[v].z, o[jj][v].z, d);
+                    d = fmaf(self[v].w, o[jj][v].w, d);
+                }
+                d = group_sum<G>(d);
+                const float w = x / fmaxf(d, 1e-10f);  // poisson_mf_cavi.py:153,157 (x = 0 past the segment end)
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    sa[v].x = fmaf(w, o[jj][v].x, sa[v].x);  sb[v].x += o[jj][v].x;
+                    sa[v].y = fmaf(w, o[jj][v].y, sa[v].y);  sb[v].y += o[jj][v].y;
+                    sa[v].z = fmaf(w, o[jj][v].z, sa[v].z);  sb[v].z += o[jj][v].z;
+                    sa[v].w = fmaf(w, o[jj][v].w, sa[v].w);  sb[v].w += o[jj][v].w;
+                }
+            }
+        }
+    }
+    if (!has) return;
+    if (pidx < 0) {  // the whole row lives in this segment: finish it here
+        gamma_row_update<G, V, HYPER>(a, R, gl, group_mask<G>(lane), self, sa, sb);
+    } else {
+        float* dst = a.partial + (size_t)pidx * 2 * a.ld;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int idx = gl + v * G;
+            if (idx < a.nvec) {
+                *reinterpret_cast<float4*>(dst + idx * 4) = sa[v];
+                *reinterpret_cast<float4*>(dst + a.ld + idx * 4) = sb[v];
+            }
+        }
+    }
+}
+
+// Rows cut into several segments: sum the partials in segment order, then the same row update.
+template <int G, int V, bool HYPER>
+__global__ void __launch_bounds__(256) gamma_multi_kernel(const GammaArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool has = gid < a.n_multi;
+    int row = 0, first = 0, last = 0;
+    if (has) {
+        row = a.multi_row[gid];
+        first = a.multi_first[gid];
+        last = a.multi_first[gid + 1];
+    }
+    const int R = a.row_offset + row;
+    float4 self[V], sa[V], sb[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int idx = gl + v * G;
+        self[v] = (has && idx < a.nvec) ? *reinterpret_cast<const float4*>(a.E_self + (size_t)R * a.ld + idx * 4) : f4_zero();
+        sa[v] = f4_zero();
+        sb[v] = f4_zero();
+    }
+    for (int q = first; q < last; ++q) {
+        const float* src = a.partial + (size_t)q * 2 * a.ld;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int idx = gl + v * G;
+            if (idx < a.nvec) {
+                const float4 pa = *reinterpret_cast<const float4*>(src + idx * 4);
+                const float4 pb = *reinterpret_cast<const float4*>(src + a.ld + idx * 4);
+                sa[v].x += pa.x; sa[v].y += pa.y; sa[v].z += pa.z; sa[v].w += pa.w;
+                sb[v].x += pb.x; sb[v].y += pb.y; sb[v].z += pb.z; sb[v].w += pb.w;
+            }
+        }
+    }
+    if (has) gamma_row_update<G, V, HYPER>(a, R, gl, group_mask<G>(lane), self, sa, sb);
+}
+
+static int g_tune_group = 0;   // 0 = auto; else forced G for nvec <= 16 (8 or 16)
+static int g_tune_unroll = 0;  // 0 = auto; else forced U
+
+template <int G, int V, int U>
+static int launch_gamma(const GammaArgs& a, bool hyper, cudaStream_t s) {
+    if (a.n_seg > 0) {
+        const unsigned grid = (unsigned)cdiv((int64_t)a.n_seg * G, 256);
+        if (hyper) gamma_pass_kernel<G, V, U, true><<<grid, 256, 0, s>>>(a);
+        else gamma_pass_kernel<G, V, U, false><<<grid, 256, 0, s>>>(a);
+        PMF_LAUNCH_CHECK();
+    }
+    if (a.n_multi > 0) {
+        const unsigned grid = (unsigned)cdiv((int64_t)a.n_multi * G, 256);
+        if (hyper) gamma_multi_kernel<G, V, true><<<grid, 256, 0, s>>>(a);
+        else gamma_multi_kernel<G, V, false><<<grid, 256, 0, s>>>(a);
+        PMF_LAUNCH_CHECK();
+    }
+    return PMF_OK;
+}
+
+}  // namespace pmf
+
+using namespace pmf;
+
+extern "C" {
+
+int pmf_tune(const char* key, int value) {
+    PMF_REQUIRE(key != nullptr, "key is NULL");
+    if (!strcmp(key, "gamma_group")) g_tune_group = value;
+    else if (!strcmp(key, "gamma_unroll")) g_tune_unroll = value;
+    else { set_error("unknown tuning key '%s'", key); return PMF_EINVAL; }
+    return PMF_OK;
+}
+
+int64_t pmf_gamma_pass_workspace_bytes(const pmf_csr* csr, int32_t ld) {
+    if (!csr || ld <= 0) return -1;
+    const CsrView c = csr_view(csr);
+    const int64_t b = (int64_t)c.n_partial * 2 * ld * (int64_t)sizeof(float);
+    return b > 0 ? b : 16;
+}
+
+int pmf_gamma_pass(const pmf_csr* csr, int32_t K, int32_t ld, const float* d_E_oth, float* d_E_self, float* d_shp,
+                   float* d_rte, float shape_prior, float rate_prior, const float* d_rate_prior_vec,
+                   float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior,
+                   void* d_workspace, void* stream) {
+    PMF_REQUIRE(csr != nullptr, "csr is NULL");
+    PMF_REQUIRE(K >= 1 && ld >= K && ld % 8 == 0 && ld <= 256, "need 1 <= K <= ld <= 256 and ld %% 8 == 0 (K=%d ld=%d)", K, ld);
+    PMF_REQUIRE(d_E_oth && d_E_self, "factor tables are NULL");
+    PMF_REQUIRE((d_hyper_rate == nullptr) == (d_hyper_mean == nullptr), "hyper_rate and hyper_mean go together");
+    const CsrView c = csr_view(csr);
+    PMF_REQUIRE(c.n_partial == 0 || d_workspace != nullptr, "workspace is NULL but %d partial sums are needed", c.n_partial);
+    GammaArgs a;
+    a.seg_row = c.seg_row; a.seg_start = c.seg_start; a.seg_partial = c.seg_partial; a.row_ptr = c.row_ptr;
+    a.col = c.col; a.val = c.val; a.multi_row = c.multi_row; a.multi_first = c.multi_first;
+    a.n_seg = c.n_seg; a.n_multi = c.n_multi; a.seg_len = c.seg_len; a.row_offset = c.row_offset;
+    a.K = K; a.ld = ld; a.nvec = ld / 4;
+    a.E_oth = d_E_oth; a.E_self = d_E_self; a.shp = d_shp; a.rte = d_rte;
+    a.shape_prior = shape_prior; a.rate_prior = rate_prior; a.rate_prior_vec = d_rate_prior_vec;
+    a.hyper_rate = d_hyper_rate; a.hyper_mean = d_hyper_mean; a.hyper_shape = hyper_shape;
+    a.hyper_rate_prior = hyper_rate_prior; a.partial = (float*)d_workspace;
+    const bool hyper = d_hyper_rate != nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nv = a.nvec;
+    if (nv <= 4) return launch_gamma<4, 1, 4>(a, hyper, s);
+    if (nv <= 8) return g_tune_unroll == 4 ? launch_gamma<8, 1, 4>(a, hyper, s) : launch_gamma<8, 1, 8>(a, hyper, s);
+    if (nv <= 16) {
+        if (g_tune_group == 16) return g_tune_unroll == 8 ? launch_gamma<16, 1, 8>(a, hyper, s) : launch_gamma<16, 1, 4>(a, hyper, s);
+        if (g_tune_unroll == 8) return launch_gamma<8, 2, 8>(a, hyper, s);
+        if (g_tune_unroll == 2) return launch_gamma<8, 2, 2>(a, hyper, s);
+        return launch_gamma<8, 2, 4>(a, hyper, s);
+    }
+    if (nv <= 24) return launch_gamma<8, 3, 2>(a, hyper, s);
+    if (nv <= 32) return launch_gamma<8, 4, 2>(a, hyper, s);
+    return launch_gamma<16, 4, 2>(a, hyper, s);
+}
+
+}  // extern "C"

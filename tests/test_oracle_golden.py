@@ -121,3 +121,35 @@ def test_hpf_map_training_replay(golden):
         assert abs(tot - g["epoch_loss"][ep]) < 1e-4 * abs(g["epoch_loss"][ep])
     for k in P:
         assert rel_max(P[k], g["final_" + k]) < 2e-4, k   # fp64 restatement vs fp32 torch Adam
+
+
+# ---- the C restatement (oracle/pmf_oracle.c) against the same reference-generated vectors ----
+def test_c_oracle_grouping(golden):
+    from oracle import c_oracle as CO
+    g = golden("poisson")
+    rp, perm = CO.group(g["u"], g["n_users"])
+    assert np.array_equal(perm, g["user_perm"]) and np.array_equal(np.diff(rp), g["user_counts"])
+    rp, perm = CO.group(g["i"], g["n_items"])
+    assert np.array_equal(perm, g["item_perm"]) and np.array_equal(np.diff(rp), g["item_counts"])
+
+
+def test_c_oracle_poisson(golden):
+    from oracle import c_oracle as CO
+    g = golden("poisson")
+    init = O.poisson_init(g["n_users"], g["n_items"], g["K"], g["a0"], g["b0"], g["seed"])
+    st = CO.poisson_sweeps(g["u"], g["i"], g["x"], g["n_users"], g["n_items"], g["K"], g["a0"], g["b0"], g["T"],
+                           init["E_theta"], init["E_beta"], threads=2)
+    for k in ("a_theta", "b_theta", "a_beta", "b_beta", "E_theta", "E_beta"):
+        assert rel_max(st[k], g[k]) < TIGHT, k
+    assert rel_max(CO.predict(g["val_u"], g["val_i"], st["E_theta"], st["E_beta"]), g["val_pred"]) < TIGHT
+
+
+def test_c_oracle_hpf(golden):
+    from oracle import c_oracle as CO
+    g = golden("hpf_cavi")
+    cfg = {k: g[k] for k in ("a", "a_prime", "b_prime", "c", "c_prime", "d_prime")}
+    init = O.hpf_init(g["n_users"], g["n_items"], g["K"], cfg, g["seed"])
+    st = CO.hpf_sweeps(g["u"], g["i"], g["x"], g["n_users"], g["n_items"], g["K"], cfg, g["T"], init, threads=2)
+    for k in ("gamma_a_theta", "gamma_b_theta", "gamma_a_beta", "gamma_b_beta", "gamma_b_xi", "gamma_b_eta",
+              "E_theta", "E_beta", "E_xi", "E_eta"):
+        assert rel_max(st[k], g[k]) < TIGHT, k
