@@ -30,9 +30,9 @@ def lib():
         L = C.CDLL(LIB)
         L.orc_group.argtypes = [i32p, C.c_int64, C.c_int32, i64p, i64p]
         L.orc_poisson_sweeps.argtypes = [i32p, i32p, f64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double,
-                                         C.c_double, C.c_int32, f64p, f64p, f64p, f64p, f64p, f64p, C.c_int]
+                                         C.c_double, C.c_int32, f64p, f64p, f64p, f64p, f64p, f64p, C.c_int, C.POINTER(C.c_double)]
         L.orc_hpf_sweeps.argtypes = [i32p, i32p, f64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [C.c_double] * 6 + \
-                                    [C.c_int32] + [f64p] * 10 + [C.c_int]
+                                    [C.c_int32] + [f64p] * 10 + [C.c_int, C.POINTER(C.c_double)]
         L.orc_predict.argtypes = [i64p, i64p, C.c_int64, f64p, C.c_int32, f64p, C.c_int32, C.c_int32, f64p]
         L.orc_max_threads.restype = C.c_int
         _lib = L
@@ -57,8 +57,9 @@ def poisson_sweeps(u, i, x, N, M, K, a0, b0, sweeps, E_theta0, E_beta0, threads=
     x = np.ascontiguousarray(x, dtype=np.float64)
     Et = np.array(E_theta0, dtype=np.float64, order="C"); Eb = np.array(E_beta0, dtype=np.float64, order="C")
     at, bt, ab, bb = np.zeros_like(Et), np.zeros_like(Et), np.zeros_like(Eb), np.zeros_like(Eb)
-    lib().orc_poisson_sweeps(u, i, x, len(x), N, M, K, a0, b0, sweeps, Et, Eb, at, bt, ab, bb, threads)
-    return dict(E_theta=Et, E_beta=Eb, a_theta=at, b_theta=bt, a_beta=ab, b_beta=bb)
+    secs = C.c_double(0.0)
+    lib().orc_poisson_sweeps(u, i, x, len(x), N, M, K, a0, b0, sweeps, Et, Eb, at, bt, ab, bb, threads, C.byref(secs))
+    return dict(E_theta=Et, E_beta=Eb, a_theta=at, b_theta=bt, a_beta=ab, b_beta=bb, sweep_seconds=secs.value)
 
 
 def hpf_sweeps(u, i, x, N, M, K, cfg, sweeps, init, threads=0):
@@ -69,11 +70,12 @@ def hpf_sweeps(u, i, x, N, M, K, cfg, sweeps, init, threads=0):
     Ex = np.array(init["E_xi"], dtype=np.float64, order="C"); Ee = np.array(init["E_eta"], dtype=np.float64, order="C")
     at, bt, ab, bb = np.zeros_like(Et), np.zeros_like(Et), np.zeros_like(Eb), np.zeros_like(Eb)
     bx, be = np.zeros_like(Ex), np.zeros_like(Ee)
+    secs = C.c_double(0.0)
     lib().orc_hpf_sweeps(u, i, x, len(x), N, M, K, cfg["a"], cfg["c"], cfg["b_prime"], cfg["d_prime"],
                          float(init["gamma_a_xi"]), float(init["gamma_a_eta"]), sweeps, Et, Eb, Ex, Ee, at, bt, ab, bb,
-                         bx, be, threads)
+                         bx, be, threads, C.byref(secs))
     return dict(E_theta=Et, E_beta=Eb, E_xi=Ex, E_eta=Ee, gamma_a_theta=at, gamma_b_theta=bt, gamma_a_beta=ab,
-                gamma_b_beta=bb, gamma_b_xi=bx, gamma_b_eta=be)
+                gamma_b_beta=bb, gamma_b_xi=bx, gamma_b_eta=be, sweep_seconds=secs.value)
 
 
 def predict(users, items, F_user, F_item):

@@ -14,9 +14,11 @@
  *   orc_hpf_sweeps                               hpf_cavi.py:120-193
  *   orc_predict                                  poisson_mf_cavi.py:221-241
  */
+#define _POSIX_C_SOURCE 199309L
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -54,9 +56,11 @@ void orc_gamma_pass(const int64_t* row_ptr, const int64_t* perm, const int32_t* 
                 const int64_t t = perm[p];
                 const double* o = E_oth + (size_t)other[t] * K;
                 double rate = 0.0;
+#pragma omp simd reduction(+ : rate)
                 for (int k = 0; k < K; ++k) rate += o[k] * own[k];
                 if (rate < RATE_FLOOR) rate = RATE_FLOOR;
                 const double w = x[t] / rate;
+#pragma omp simd
                 for (int k = 0; k < K; ++k) {
                     sa[k] += w * o[k] * own[k];
                     sb[k] += o[k];
@@ -71,6 +75,12 @@ void orc_gamma_pass(const int64_t* row_ptr, const int64_t* perm, const int32_t* 
     }
 }
 
+static double now_seconds(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 static void divide(const double* a, const double* b, double* e, size_t n) {
     for (size_t k = 0; k < n; ++k) e[k] = a[k] / b[k];
 }
@@ -78,19 +88,22 @@ static void divide(const double* a, const double* b, double* e, size_t n) {
 /* In/out: E_theta (N,K), E_beta (M,K) hold the initial expectations and receive the final ones. */
 void orc_poisson_sweeps(const int32_t* u, const int32_t* i, const double* x, int64_t nnz, int32_t N, int32_t M,
                         int32_t K, double a0, double b0, int32_t sweeps, double* E_theta, double* E_beta,
-                        double* a_theta, double* b_theta, double* a_beta, double* b_beta, int threads) {
+                        double* a_theta, double* b_theta, double* a_beta, double* b_beta, int threads,
+                        double* sweep_seconds /* out, may be NULL: time of the sweep loop only */) {
     int64_t* rp_u = (int64_t*)malloc(sizeof(int64_t) * ((size_t)N + 1));
     int64_t* rp_i = (int64_t*)malloc(sizeof(int64_t) * ((size_t)M + 1));
     int64_t* pm_u = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nnz > 0 ? nnz : 1));
     int64_t* pm_i = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nnz > 0 ? nnz : 1));
     orc_group(u, nnz, N, rp_u, pm_u);
     orc_group(i, nnz, M, rp_i, pm_i);
+    const double t0 = now_seconds();
     for (int32_t s = 0; s < sweeps; ++s) {
         orc_gamma_pass(rp_u, pm_u, i, x, N, K, E_theta, E_beta, a0, b0, NULL, a_theta, b_theta, threads);
         divide(a_theta, b_theta, E_theta, (size_t)N * K);
         orc_gamma_pass(rp_i, pm_i, u, x, M, K, E_beta, E_theta, a0, b0, NULL, a_beta, b_beta, threads);
         divide(a_beta, b_beta, E_beta, (size_t)M * K);
     }
+    if (sweep_seconds) *sweep_seconds = now_seconds() - t0;
     free(rp_u); free(rp_i); free(pm_u); free(pm_i);
 }
 
@@ -98,13 +111,15 @@ void orc_poisson_sweeps(const int32_t* u, const int32_t* i, const double* x, int
 void orc_hpf_sweeps(const int32_t* u, const int32_t* i, const double* x, int64_t nnz, int32_t N, int32_t M,
                     int32_t K, double a, double c, double b_prime, double d_prime, double a_xi, double a_eta,
                     int32_t sweeps, double* E_theta, double* E_beta, double* E_xi, double* E_eta, double* a_theta,
-                    double* b_theta, double* a_beta, double* b_beta, double* b_xi, double* b_eta, int threads) {
+                    double* b_theta, double* a_beta, double* b_beta, double* b_xi, double* b_eta, int threads,
+                    double* sweep_seconds /* out, may be NULL */) {
     int64_t* rp_u = (int64_t*)malloc(sizeof(int64_t) * ((size_t)N + 1));
     int64_t* rp_i = (int64_t*)malloc(sizeof(int64_t) * ((size_t)M + 1));
     int64_t* pm_u = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nnz > 0 ? nnz : 1));
     int64_t* pm_i = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nnz > 0 ? nnz : 1));
     orc_group(u, nnz, N, rp_u, pm_u);
     orc_group(i, nnz, M, rp_i, pm_i);
+    const double t0 = now_seconds();
     for (int32_t s = 0; s < sweeps; ++s) {
         orc_gamma_pass(rp_u, pm_u, i, x, N, K, E_theta, E_beta, a, 0.0, E_xi, a_theta, b_theta, threads);
         divide(a_theta, b_theta, E_theta, (size_t)N * K);
@@ -123,6 +138,7 @@ void orc_hpf_sweeps(const int32_t* u, const int32_t* i, const double* x, int64_t
             E_eta[r] = a_eta / b_eta[r];
         }
     }
+    if (sweep_seconds) *sweep_seconds = now_seconds() - t0;
     free(rp_u); free(rp_i); free(pm_u); free(pm_i);
 }
 

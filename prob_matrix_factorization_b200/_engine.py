@@ -21,13 +21,21 @@ def row_stride(K):
     return _cabi.load().pmf_row_stride(int(K))
 
 
-def pad_table(host, ld, device, pinned=False):
-    """float64/32 (R, K) host array -> float32 (R, ld) CUDA tensor, zero padded."""
+def pad_table(host, ld, device):
+    """(R, K) host array (float64 or float32) -> float32 (R, ld) CUDA tensor, zero padded.
+
+    The H2D copy is issued straight from the caller's buffer (asynchronous when that memory is
+    pinned); the cast and the padding run on the device.
+    """
     host = np.asarray(host)
     R, K = host.shape
-    buf = torch.zeros((R, ld), dtype=torch.float32, pin_memory=pinned)
-    buf[:, :K] = torch.from_numpy(np.ascontiguousarray(host, dtype=np.float32))
-    return buf.to(device, non_blocking=True)
+    src = torch.from_numpy(np.ascontiguousarray(host))
+    if src.dtype == torch.float32 and K == ld:
+        return src.to(device, non_blocking=True)
+    dev = src.to(device, non_blocking=True)
+    out = torch.zeros((R, ld), dtype=torch.float32, device=device)
+    out[:, :K] = dev
+    return out
 
 
 def table_to_host(t, K, dtype=np.float64):
@@ -165,6 +173,17 @@ class GammaEngine:
         if self.hyper is not None:
             self.E_xi.copy_(to_device(np.asarray(E_xi, dtype=np.float32), self.dev))
             self.E_eta.copy_(to_device(np.asarray(E_eta, dtype=np.float32), self.dev))
+
+    def download_means(self, out_theta, out_beta):
+        """Copy E_theta / E_beta (first K columns) into caller-provided (pinned) float32 host tensors."""
+        K = self.K
+        if self.ld == K:
+            out_theta.copy_(self.E_theta, non_blocking=True)
+            out_beta.copy_(self.E_beta, non_blocking=True)
+        else:
+            out_theta.copy_(self.E_theta[:, :K], non_blocking=True)
+            out_beta.copy_(self.E_beta[:, :K], non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
 
     # -- one pass ------------------------------------------------------------------------------
     def _pass(self, grouped, E_oth, E_self, shp, rte, shape_prior, rate_prior, rate_vec, hyper_rate, hyper_mean,
