@@ -187,6 +187,48 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const int32
     }
 }
 
+// Stable sort of (key, index) pairs by key in [0, 2^bits): d_sorted_keys / d_perm receive the result.
+// perm[p] = original position of the p-th smallest key (ties in input order).
+static int stable_sort_by_key(const int32_t* d_key, int64_t n, int bits, int32_t* d_sorted_keys, int32_t* d_perm,
+                              cudaStream_t s) {
+    const int passes = (bits + 7) / 8 > 0 ? (bits + 7) / 8 : 1;
+    const int n_tiles = (int)cdiv(n, kSortTile);
+    int32_t *k1 = nullptr, *v1 = nullptr, *hist = nullptr;
+    PMF_TRY(alloc_async(&hist, (int64_t)256 * n_tiles, s));
+    if (passes > 1) {
+        PMF_TRY(alloc_async(&k1, n, s));
+        PMF_TRY(alloc_async(&v1, n, s));
+    }
+    // ping-pong so that the LAST pass lands in (d_sorted_keys, d_perm)
+    const int32_t* kin = d_key;
+    const int32_t* vin = nullptr;
+    for (int p = 0; p < passes; ++p) {
+        const bool to_final = ((passes - 1 - p) % 2) == 0;
+        int32_t* kout = to_final ? d_sorted_keys : k1;
+        int32_t* vout = to_final ? d_perm : v1;
+        radix_hist_kernel<<<n_tiles, kSortThreads, 0, s>>>(kin, n, 8 * p, hist, n_tiles);
+        PMF_LAUNCH_CHECK();
+        PMF_TRY(exclusive_scan_i32(hist, hist, (int64_t)256 * n_tiles, nullptr, s));
+        if (p == 0)
+            radix_scatter_kernel<true><<<n_tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, 8 * p, hist, n_tiles);
+        else
+            radix_scatter_kernel<false><<<n_tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, 8 * p, hist, n_tiles);
+        PMF_LAUNCH_CHECK();
+        kin = kout;
+        vin = vout;
+    }
+    free_async(k1, s);
+    free_async(v1, s);
+    free_async(hist, s);
+    return PMF_OK;
+}
+
+static int bit_length(int64_t max_value) {
+    int bits = 1;
+    while (bits < 31 && (1ll << bits) <= max_value) ++bits;
+    return bits;
+}
+
 // row_ptr from sorted keys: the thread at position p closes every row in (key[p-1], key[p]]
 __global__ void row_ptr_kernel(const int32_t* __restrict__ sorted_keys, int64_t n, int32_t n_rows,
                                int32_t* __restrict__ row_ptr) {
@@ -259,6 +301,17 @@ __global__ void seg_fill_kernel(const int32_t* __restrict__ row_ptr, int32_t n_r
     }
 }
 
+// sort key of a segment: seg_len - (its length), so that an ascending stable sort lists long segments first
+__global__ void seg_key_kernel(const int32_t* __restrict__ seg_row, const int32_t* __restrict__ seg_start,
+                               const int32_t* __restrict__ row_ptr, int32_t n_seg, int32_t seg_len,
+                               int32_t* __restrict__ key) {
+    const int32_t sidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sidx >= n_seg) return;
+    const int32_t b = seg_start[sidx];
+    const int32_t e = min(b + seg_len, row_ptr[seg_row[sidx] + 1]);
+    key[sidx] = seg_len - (e - b);
+}
+
 __global__ void rebase_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int32_t n, int32_t base) {
     const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] - base;
@@ -275,6 +328,7 @@ struct pmf_csr {
     int32_t *row_ptr = nullptr, *perm = nullptr, *col = nullptr;
     float* val = nullptr;
     int32_t *seg_row = nullptr, *seg_start = nullptr, *seg_partial = nullptr;
+    int32_t* seg_order = nullptr;  // segment ids, longest first: a warp's groups get equally long segments
     int32_t *multi_row = nullptr, *multi_first = nullptr;
     int64_t bytes = 0;
 };
@@ -323,6 +377,19 @@ static int build_segments(pmf_csr* c, cudaStream_t s) {
     free_async(multi_flag, s);
     free_async(part_cnt, s);
     free_async(totals, s);
+    // processing order: segments sorted by length, longest first (stable -> deterministic)
+    PMF_TRY(dev_alloc((void**)&c->seg_order, (int64_t)c->n_seg * 4, c));
+    if (c->n_seg > 0) {
+        int32_t *key = nullptr, *sorted = nullptr;
+        PMF_TRY(alloc_async(&key, c->n_seg, s));
+        PMF_TRY(alloc_async(&sorted, c->n_seg, s));
+        seg_key_kernel<<<(unsigned)cdiv(c->n_seg, 256), 256, 0, s>>>(c->seg_row, c->seg_start, c->row_ptr, c->n_seg,
+                                                                     c->seg_len, key);
+        PMF_LAUNCH_CHECK();
+        PMF_TRY(stable_sort_by_key(key, c->n_seg, bit_length(c->seg_len), sorted, c->seg_order, s));
+        free_async(key, s);
+        free_async(sorted, s);
+    }
     PMF_CUDA(cudaStreamSynchronize(s));
     return PMF_OK;
 }
@@ -350,8 +417,8 @@ int pmf_row_stride(int K) { return K <= 0 ? 0 : ((K + 7) / 8) * 8; }
 
 int pmf_csr_free(pmf_csr* c) {
     if (!c) return PMF_OK;
-    void* ptrs[] = {c->row_ptr, c->perm, c->col, c->val, c->seg_row, c->seg_start, c->seg_partial, c->multi_row,
-                    c->multi_first};
+    void* ptrs[] = {c->row_ptr, c->perm, c->col, c->val, c->seg_row, c->seg_start, c->seg_partial, c->seg_order,
+                    c->multi_row, c->multi_first};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete c;
@@ -364,7 +431,7 @@ int pmf_csr_build(const int32_t* d_key, const int32_t* d_other, const float* d_v
     *out = nullptr;
     PMF_REQUIRE(nnz >= 0 && nnz < (int64_t)INT32_MAX, "nnz=%lld out of range", (long long)nnz);
     PMF_REQUIRE(n_rows > 0, "n_rows=%d must be positive", n_rows);
-    PMF_REQUIRE(seg_len >= 8 && seg_len % 8 == 0, "seg_len=%d must be a positive multiple of 8", seg_len);
+    PMF_REQUIRE(seg_len >= 8 && seg_len % 8 == 0 && seg_len <= 65536, "seg_len=%d must be a multiple of 8 in [8, 65536]", seg_len);
     PMF_REQUIRE(nnz == 0 || (d_key && d_other && d_val), "NULL input with nnz > 0");
     cudaStream_t s = (cudaStream_t)stream;
     pmf_csr* c = new pmf_csr();
@@ -396,43 +463,14 @@ int pmf_csr_build(const int32_t* d_key, const int32_t* d_other, const float* d_v
             free_async(bad, s);
             PMF_REQUIRE(h_bad == 0, "ids out of range: keys must lie in [0, %d), other ids must be >= 0", n_rows);
 
-            int bits = 1;
-            while (bits < 31 && (1ll << bits) < (int64_t)n_rows) ++bits;
-            const int passes = (bits + 7) / 8;
-            const int n_tiles = (int)cdiv(nnz, kSortTile);
-            int32_t *k0 = nullptr, *k1 = nullptr, *v1 = nullptr, *hist = nullptr;
+            int32_t* k0 = nullptr;
             PMF_TRY(alloc_async(&k0, nnz, s));
-            PMF_TRY(alloc_async(&hist, (int64_t)256 * n_tiles, s));
-            if (passes > 1) {
-                PMF_TRY(alloc_async(&k1, nnz, s));
-                PMF_TRY(alloc_async(&v1, nnz, s));
-            }
-            // ping-pong so that the LAST pass lands in (k0, c->perm)
-            const int32_t* kin = d_key;
-            const int32_t* vin = nullptr;
-            for (int p = 0; p < passes; ++p) {
-                const bool to_final = ((passes - 1 - p) % 2) == 0;
-                int32_t* kout = to_final ? k0 : k1;
-                int32_t* vout = to_final ? c->perm : v1;
-                radix_hist_kernel<<<n_tiles, kSortThreads, 0, s>>>(kin, nnz, 8 * p, hist, n_tiles);
-                PMF_LAUNCH_CHECK();
-                PMF_TRY(exclusive_scan_i32(hist, hist, (int64_t)256 * n_tiles, nullptr, s));
-                if (p == 0)
-                    radix_scatter_kernel<true><<<n_tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, nnz, 8 * p, hist, n_tiles);
-                else
-                    radix_scatter_kernel<false><<<n_tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, nnz, 8 * p, hist, n_tiles);
-                PMF_LAUNCH_CHECK();
-                kin = kout;
-                vin = vout;
-            }
+            PMF_TRY(stable_sort_by_key(d_key, nnz, bit_length((int64_t)n_rows - 1), k0, c->perm, s));
             row_ptr_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(k0, nnz, n_rows, c->row_ptr);
             PMF_LAUNCH_CHECK();
             gather_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(c->perm, d_other, d_val, nnz, c->col, c->val);
             PMF_LAUNCH_CHECK();
             free_async(k0, s);
-            free_async(k1, s);
-            free_async(v1, s);
-            free_async(hist, s);
             return PMF_OK;
         };
         if ((st = body()) != PMF_OK) return fail(st);
@@ -519,6 +557,7 @@ int pmf_csr_partition(const pmf_csr* c, int32_t parts, int32_t* h_bounds) {
 namespace pmf {
 CsrView csr_view(const pmf_csr* c) {
     return CsrView{c->nnz, c->n_rows, c->row_offset, c->seg_len, c->n_seg, c->n_multi, c->n_partial, c->row_ptr,
-                   c->col, c->val, c->seg_row, c->seg_start, c->seg_partial, c->multi_row, c->multi_first};
+                   c->col, c->val, c->seg_row, c->seg_start, c->seg_partial, c->seg_order, c->multi_row,
+                   c->multi_first};
 }
 }  // namespace pmf

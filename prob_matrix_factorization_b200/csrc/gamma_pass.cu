@@ -22,7 +22,7 @@
 namespace pmf {
 
 struct GammaArgs {
-    const int32_t *seg_row, *seg_start, *seg_partial, *row_ptr, *col;
+    const int32_t *seg_row, *seg_start, *seg_partial, *seg_order, *row_ptr, *col;
     const float* val;
     const int32_t *multi_row, *multi_first;
     int32_t n_seg, n_multi, seg_len, row_offset, K, ld, nvec;
@@ -103,10 +103,12 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
     const bool has = gid < a.n_seg;
     int row = 0, p = 0, end = 0, pidx = -1;
     if (has) {
-        row = a.seg_row[gid];
-        p = a.seg_start[gid];
+        // segments are visited longest first, so the groups sharing a warp run (nearly) equal trip counts
+        const int sidx = a.seg_order[gid];
+        row = a.seg_row[sidx];
+        p = a.seg_start[sidx];
         end = min(p + a.seg_len, a.row_ptr[row + 1]);
-        pidx = a.seg_partial[gid];
+        pidx = a.seg_partial[sidx];
     }
     const int R = a.row_offset + row;
     float4 self[V], sa[V], sb[V];
@@ -179,42 +181,53 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
     }
 }
 
-// Rows cut into several segments: sum the partials in segment order, then the same row update.
+// Rows cut into several segments: one WARP per row.  The 32/G groups of the warp each sum every
+// (32/G)-th partial (independent loads in flight), the group sums are folded with shuffles in a fixed
+// order, and group 0 applies the same row update.  Deterministic; no atomics.
 template <int G, int V, bool HYPER>
 __global__ void __launch_bounds__(256) gamma_multi_kernel(const GammaArgs a) {
+    constexpr int NG = 32 / G;
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);
-    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const bool has = gid < a.n_multi;
-    int row = 0, first = 0, last = 0;
-    if (has) {
-        row = a.multi_row[gid];
-        first = a.multi_first[gid];
-        last = a.multi_first[gid + 1];
-    }
+    const int grp = lane / G;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= a.n_multi) return;  // warp-uniform
+    const int row = a.multi_row[wid];
+    const int first = a.multi_first[wid], last = a.multi_first[wid + 1];
     const int R = a.row_offset + row;
     float4 self[V], sa[V], sb[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         const int idx = gl + v * G;
-        self[v] = (has && idx < a.nvec) ? *reinterpret_cast<const float4*>(a.E_self + (size_t)R * a.ld + idx * 4) : f4_zero();
+        self[v] = (idx < a.nvec) ? *reinterpret_cast<const float4*>(a.E_self + (size_t)R * a.ld + idx * 4) : f4_zero();
         sa[v] = f4_zero();
         sb[v] = f4_zero();
     }
-    for (int q = first; q < last; ++q) {
+    for (int q = first + grp; q < last; q += NG) {
         const float* src = a.partial + (size_t)q * 2 * a.ld;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             const int idx = gl + v * G;
             if (idx < a.nvec) {
-                const float4 pa = *reinterpret_cast<const float4*>(src + idx * 4);
-                const float4 pb = *reinterpret_cast<const float4*>(src + a.ld + idx * 4);
+                const float4 pa = ld_stream_f4(src + idx * 4);
+                const float4 pb = ld_stream_f4(src + a.ld + idx * 4);
                 sa[v].x += pa.x; sa[v].y += pa.y; sa[v].z += pa.z; sa[v].w += pa.w;
                 sb[v].x += pb.x; sb[v].y += pb.y; sb[v].z += pb.z; sb[v].w += pb.w;
             }
         }
     }
-    if (has) gamma_row_update<G, V, HYPER>(a, R, gl, group_mask<G>(lane), self, sa, sb);
+    __syncwarp();
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) {   // fold the groups: lanes with equal gl hold the same K-slice
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            sa[v].x += __shfl_xor_sync(0xffffffffu, sa[v].x, o);  sb[v].x += __shfl_xor_sync(0xffffffffu, sb[v].x, o);
+            sa[v].y += __shfl_xor_sync(0xffffffffu, sa[v].y, o);  sb[v].y += __shfl_xor_sync(0xffffffffu, sb[v].y, o);
+            sa[v].z += __shfl_xor_sync(0xffffffffu, sa[v].z, o);  sb[v].z += __shfl_xor_sync(0xffffffffu, sb[v].z, o);
+            sa[v].w += __shfl_xor_sync(0xffffffffu, sa[v].w, o);  sb[v].w += __shfl_xor_sync(0xffffffffu, sb[v].w, o);
+        }
+    }
+    if (grp == 0) gamma_row_update<G, V, HYPER>(a, R, gl, group_mask<G>(lane), self, sa, sb);
 }
 
 static int g_tune_group = 0;   // 0 = auto; else forced G for nvec <= 16 (8 or 16)
@@ -229,7 +242,7 @@ static int launch_gamma(const GammaArgs& a, bool hyper, cudaStream_t s) {
         PMF_LAUNCH_CHECK();
     }
     if (a.n_multi > 0) {
-        const unsigned grid = (unsigned)cdiv((int64_t)a.n_multi * G, 256);
+        const unsigned grid = (unsigned)cdiv((int64_t)a.n_multi * 32, 256);
         if (hyper) gamma_multi_kernel<G, V, true><<<grid, 256, 0, s>>>(a);
         else gamma_multi_kernel<G, V, false><<<grid, 256, 0, s>>>(a);
         PMF_LAUNCH_CHECK();
@@ -269,7 +282,8 @@ int pmf_gamma_pass(const pmf_csr* csr, int32_t K, int32_t ld, const float* d_E_o
     const CsrView c = csr_view(csr);
     PMF_REQUIRE(c.n_partial == 0 || d_workspace != nullptr, "workspace is NULL but %d partial sums are needed", c.n_partial);
     GammaArgs a;
-    a.seg_row = c.seg_row; a.seg_start = c.seg_start; a.seg_partial = c.seg_partial; a.row_ptr = c.row_ptr;
+    a.seg_row = c.seg_row; a.seg_start = c.seg_start; a.seg_partial = c.seg_partial; a.seg_order = c.seg_order;
+    a.row_ptr = c.row_ptr;
     a.col = c.col; a.val = c.val; a.multi_row = c.multi_row; a.multi_first = c.multi_first;
     a.n_seg = c.n_seg; a.n_multi = c.n_multi; a.seg_len = c.seg_len; a.row_offset = c.row_offset;
     a.K = K; a.ld = ld; a.nvec = ld / 4;
@@ -284,9 +298,9 @@ int pmf_gamma_pass(const pmf_csr* csr, int32_t K, int32_t ld, const float* d_E_o
     if (nv <= 8) return g_tune_unroll == 4 ? launch_gamma<8, 1, 4>(a, hyper, s) : launch_gamma<8, 1, 8>(a, hyper, s);
     if (nv <= 16) {
         if (g_tune_group == 16) return g_tune_unroll == 8 ? launch_gamma<16, 1, 8>(a, hyper, s) : launch_gamma<16, 1, 4>(a, hyper, s);
-        if (g_tune_unroll == 8) return launch_gamma<8, 2, 8>(a, hyper, s);
+        if (g_tune_unroll == 4) return launch_gamma<8, 2, 4>(a, hyper, s);
         if (g_tune_unroll == 2) return launch_gamma<8, 2, 2>(a, hyper, s);
-        return launch_gamma<8, 2, 4>(a, hyper, s);
+        return launch_gamma<8, 2, 8>(a, hyper, s);   // measured best on C5 (profiles/README.md)
     }
     if (nv <= 24) return launch_gamma<8, 3, 2>(a, hyper, s);
     if (nv <= 32) return launch_gamma<8, 4, 2>(a, hyper, s);

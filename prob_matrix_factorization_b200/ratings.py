@@ -14,7 +14,18 @@ import torch
 
 from . import _cabi
 
-DEFAULT_SEG_LEN = 128
+DEFAULT_SEG_LEN = None  # None = auto_seg_len(nnz)
+
+
+def auto_seg_len(nnz):
+    """Longest run of observations one lane group handles alone.
+
+    Rows longer than this are cut into segments whose partial sums are combined by a second kernel.
+    Long segments are fine for throughput (segments are scheduled longest first); the cap only has to
+    keep enough independent segments for ~150 SMs x 64 groups: nnz/32768 clamped to [64, 1024].
+    """
+    want = (int(nnz) // 32768 + 7) // 8 * 8
+    return max(64, min(1024, want))
 
 
 def as_id_array(a, name):
@@ -44,6 +55,8 @@ class Grouped:
 
     @classmethod
     def build(cls, key, other, val, n_rows, seg_len=DEFAULT_SEG_LEN):
+        if seg_len is None:
+            seg_len = auto_seg_len(key.numel())
         assert key.is_cuda and key.dtype == torch.int32 and other.dtype == torch.int32 and val.dtype == torch.float32
         out = C.c_void_p()
         with torch.cuda.device(key.device):
@@ -134,6 +147,8 @@ class DeviceRatings:
             raise ValueError("u, i, rating must have equal length")
         self.nnz = u_d.numel()
         self.h2d_bytes = self.nnz * 12
+        if seg_len is None:
+            seg_len = auto_seg_len(self.nnz)
         with torch.cuda.device(device):
             by_user = Grouped.build(u_d, i_d, x_d, self.n_users, seg_len)
             by_item = Grouped.build(i_d, u_d, x_d, self.n_items, seg_len)
