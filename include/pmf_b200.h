@@ -128,6 +128,27 @@ int pmf_eval_stats(const int32_t* d_users, const int32_t* d_items, const float* 
                    int32_t K, int32_t ld, const float* d_b_user, const float* d_b_item,
                    float global_mean, int32_t drop_invalid, double* d_out, void* stream);
 
+/* ---- a5: Gaussian MF CAVI ---------------------------------------------------------------
+ * Tables per side: means m[R, ld] (ld = pmf_row_stride(K)); covariances V and second moments
+ * Q = V + m m^T as packed lower triangles [R, ldq] (ldq = pmf_gauss_packed_stride(K); element (i,j),
+ * i >= j, at i(i+1)/2 + j); biases b[R] (NULL for the no-bias model gaussian_mf_cavi.py).
+ *
+ * pmf_gauss_factor_pass replaces gaussian_mf_cavi_bias.py:132-165 / :170-201 (gaussian_mf_cavi.py:121-178):
+ *     S = sum_t Q_oth[col_t];  V[R] = inv(I/eta2 + S/sigma2)   (np.linalg.inv -> float64 Cholesky inverse)
+ *     m[R] = V[R] sum_t (val_t - b_self[R] - b_oth[col_t]) m_oth[col_t] / sigma2;  Q[R] = V[R] + m m^T
+ * rows without observations keep their state.  In place on the self tables (Jacobi: a row reads only
+ * its own bias on the self side).  d_workspace: pmf_gauss_workspace_bytes() bytes.
+ * pmf_gauss_bias_pass replaces :206-232 / :237-263:
+ *     b_self[R] = sum_t (val_t - b_oth[col_t] - <m_self[R], m_oth[col_t]>) / sigma2 / (1/eta_b2 + n_R/sigma2)
+ */
+int pmf_gauss_packed_stride(int K);
+int64_t pmf_gauss_workspace_bytes(const pmf_csr* csr, int32_t K);
+int pmf_gauss_factor_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_Q_oth,
+                          const float* d_b_oth, float* d_m_self, float* d_V_self, float* d_Q_self,
+                          const float* d_b_self, float sigma2, float eta2, void* d_workspace, void* stream);
+int pmf_gauss_bias_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_m_self,
+                        const float* d_b_oth, float* d_b_self, float sigma2, float eta_b2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,10 @@ _PROTOTYPES = {
     "pmf_gamma_pass_workspace_bytes": (C.c_int64, [VP, C.c_int32]),
     "pmf_gamma_pass": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP, VP, VP, C.c_float, C.c_float, VP,
                                  VP, VP, C.c_float, C.c_float, VP, VP]),
+    "pmf_gauss_packed_stride": (C.c_int, [C.c_int]),
+    "pmf_gauss_workspace_bytes": (C.c_int64, [VP, C.c_int32]),
+    "pmf_gauss_factor_pass": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, VP, VP, C.c_float, C.c_float, VP, VP]),
+    "pmf_gauss_bias_pass": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, C.c_float, C.c_float, VP]),
     "pmf_predict": (C.c_int, [VP, VP, C.c_int64, VP, C.c_int32, VP, C.c_int32, C.c_int32, C.c_int32,
                               VP, VP, C.c_float, C.c_int32, VP, VP]),
     "pmf_eval_stats": (C.c_int, [VP, VP, VP, VP, C.c_int32, C.c_int64, VP, C.c_int32, VP, C.c_int32,

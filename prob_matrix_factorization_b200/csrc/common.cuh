@@ -63,7 +63,7 @@ struct CsrView {
     int32_t n_rows, row_offset, seg_len, n_seg, n_multi, n_partial;
     const int32_t *row_ptr, *col;
     const float* val;
-    const int32_t *seg_row, *seg_start, *seg_partial, *seg_order, *multi_row, *multi_first;
+    const int32_t *seg_row, *seg_start, *seg_partial, *seg_order, *row_seg, *multi_row, *multi_first;
 };
 CsrView csr_view(const pmf_csr* c);
 

@@ -329,6 +329,7 @@ struct pmf_csr {
     float* val = nullptr;
     int32_t *seg_row = nullptr, *seg_start = nullptr, *seg_partial = nullptr;
     int32_t* seg_order = nullptr;  // segment ids, longest first: a warp's groups get equally long segments
+    int32_t* row_seg = nullptr;    // [n_rows+1] first segment of each row
     int32_t *multi_row = nullptr, *multi_first = nullptr;
     int64_t bytes = 0;
 };
@@ -373,6 +374,9 @@ static int build_segments(pmf_csr* c, cudaStream_t s) {
                                          c->n_partial, c->seg_row, c->seg_start, c->seg_partial, c->multi_row,
                                          c->multi_first);
     PMF_LAUNCH_CHECK();
+    PMF_TRY(dev_alloc((void**)&c->row_seg, ((int64_t)R + 1) * 4, c));
+    PMF_CUDA(cudaMemcpyAsync(c->row_seg, seg_cnt, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
+    PMF_CUDA(cudaMemcpyAsync(c->row_seg + R, &c->n_seg, 4, cudaMemcpyHostToDevice, s));
     free_async(seg_cnt, s);
     free_async(multi_flag, s);
     free_async(part_cnt, s);
@@ -418,7 +422,7 @@ int pmf_row_stride(int K) { return K <= 0 ? 0 : ((K + 7) / 8) * 8; }
 int pmf_csr_free(pmf_csr* c) {
     if (!c) return PMF_OK;
     void* ptrs[] = {c->row_ptr, c->perm, c->col, c->val, c->seg_row, c->seg_start, c->seg_partial, c->seg_order,
-                    c->multi_row, c->multi_first};
+                    c->row_seg, c->multi_row, c->multi_first};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete c;
@@ -557,7 +561,7 @@ int pmf_csr_partition(const pmf_csr* c, int32_t parts, int32_t* h_bounds) {
 namespace pmf {
 CsrView csr_view(const pmf_csr* c) {
     return CsrView{c->nnz, c->n_rows, c->row_offset, c->seg_len, c->n_seg, c->n_multi, c->n_partial, c->row_ptr,
-                   c->col, c->val, c->seg_row, c->seg_start, c->seg_partial, c->seg_order, c->multi_row,
-                   c->multi_first};
+                   c->col, c->val, c->seg_row, c->seg_start, c->seg_partial, c->seg_order, c->row_seg,
+                   c->multi_row, c->multi_first};
 }
 }  // namespace pmf

@@ -1,0 +1,299 @@
+// a5: Gaussian MF CAVI passes (with and without biases).
+//
+// Reference loops replaced: gaussian_mf_cavi_bias.py:132-165 (users), :170-201 (items), :206-232 and
+// :237-263 (biases); gaussian_mf_cavi.py:121-178 (no-bias variant = NULL bias vectors, no bias passes).
+//
+// Data layout.  Per side: means m[R, ld] (ld = K rounded up to 8, padding zero), covariances as packed
+// lower triangles V[R, ldq] (ldq = K(K+1)/2 rounded up to 8; element (i,j), i >= j, at i(i+1)/2 + j) and
+// second moments Q = V + m m^T in the same packed layout.  What the other side gathers per rating is
+// exactly the reference's E[b b^T] = V + m m^T (:151), so Q is stored ready-made by the row update that
+// produces V and m; V itself is output only.  Biases b[R].
+//
+// Factor pass = two kernels:
+//   gauss_accumulate_kernel  one CTA per segment; thread s owns float4 slot s of the concatenated row
+//                            [Q (ldq/4 slots) | m (ld/4 slots)] and sums it over the segment's ratings
+//                            (Q unweighted, m weighted by the residual x - b_self - b_oth): pure
+//                            gather + elementwise accumulate, HBM-bound, 4(ldq+ld)+12 bytes per rating.
+//   gauss_solve_kernel       one CTA per row: adds the row's segment sums in order, forms
+//                            P = I/eta2 + S/sigma2 in float64 shared memory, inverts it by Cholesky
+//                            (np.linalg.inv in the reference, :158), m = V rhs / sigma2, writes m, V, Q.
+// Rows without ratings are skipped (state kept, :134-135).
+#include "common.cuh"
+
+namespace pmf {
+
+struct GaussArgs {
+    const int32_t *seg_row, *seg_start, *seg_order, *row_ptr, *row_seg, *col;
+    const float* val;
+    int32_t n_seg, n_rows, seg_len, row_offset, K, ld, ldq, nq4, nm4;
+    const float *m_oth, *Q_oth, *b_oth, *b_self;
+    float *m_self, *V_self, *Q_self;
+    float sigma2, eta2;
+    float* scratch;  // [n_seg][ldq + ld]
+};
+
+template <int V>
+__global__ void gauss_accumulate_kernel(const GaussArgs a) {
+    const int sidx = a.seg_order[blockIdx.x];
+    const int row = a.seg_row[sidx];
+    const int p0 = a.seg_start[sidx];
+    const int p1 = min(p0 + a.seg_len, a.row_ptr[row + 1]);
+    const int T = blockDim.x;
+    const int nslots = a.nq4 + a.nm4;
+    const float bs = a.b_self ? a.b_self[a.row_offset + row] : 0.f;
+    float4 acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int p = p0; p < p1; ++p) {
+        const int c = __ldg(a.col + p);
+        const float res = __ldg(a.val + p) - bs - (a.b_oth ? __ldg(a.b_oth + c) : 0.f);
+        const float* qrow = a.Q_oth + (size_t)c * a.ldq;
+        const float* mrow = a.m_oth + (size_t)c * a.ld;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int s = threadIdx.x + v * T;
+            if (s < nslots) {
+                const bool isq = s < a.nq4;
+                const float4 r = isq ? ldg_f4(qrow + 4 * s) : ldg_f4(mrow + 4 * (s - a.nq4));
+                const float w = isq ? 1.f : res;
+                acc[v].x = fmaf(w, r.x, acc[v].x);
+                acc[v].y = fmaf(w, r.y, acc[v].y);
+                acc[v].z = fmaf(w, r.z, acc[v].z);
+                acc[v].w = fmaf(w, r.w, acc[v].w);
+            }
+        }
+    }
+    float* dst = a.scratch + (size_t)sidx * (a.ldq + a.ld);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int s = threadIdx.x + v * T;
+        if (s < nslots) *reinterpret_cast<float4*>(dst + 4 * s) = acc[v];
+    }
+}
+
+constexpr int kSolveThreads = 64;
+
+// One CTA per row.  Shared: A[K][K+1] float64 (P, then L, then L^-1), rhs[K], mean[K].
+__global__ void __launch_bounds__(kSolveThreads) gauss_solve_kernel(const GaussArgs a) {
+    extern __shared__ double sm[];
+    const int K = a.K, LD = K + 1;
+    double* A = sm;
+    double* rhs = A + (size_t)K * LD;
+    double* mean = rhs + K;
+    const int row = blockIdx.x;
+    const int s0 = a.row_seg[row], s1 = a.row_seg[row + 1];
+    if (a.row_ptr[row + 1] == a.row_ptr[row]) return;  // no ratings: keep the state
+    const int tid = threadIdx.x;
+    const int W = a.ldq + a.ld;
+    const int npk = K * (K + 1) / 2;
+    // P = I/eta2 + S/sigma2 (lower triangle), rhs = sum res*m
+    for (int e = tid; e < npk + K; e += kSolveThreads) {
+        const int off = e < npk ? e : a.ldq + (e - npk);
+        double s = 0.0;
+        for (int sg = s0; sg < s1; ++sg) s += (double)a.scratch[(size_t)sg * W + off];
+        if (e < npk) {
+            int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            while ((i + 1) * (i + 2) / 2 <= e) ++i;
+            while (i * (i + 1) / 2 > e) --i;
+            const int j = e - i * (i + 1) / 2;
+            A[i * LD + j] = s / (double)a.sigma2 + (i == j ? 1.0 / (double)a.eta2 : 0.0);
+        } else {
+            rhs[e - npk] = s;
+        }
+    }
+    __syncthreads();
+    // Cholesky P = L L^T, in place in the lower triangle
+    for (int k = 0; k < K; ++k) {
+        if (tid == 0) A[k * LD + k] = sqrt(A[k * LD + k]);
+        __syncthreads();
+        const double d = A[k * LD + k];
+        for (int i = k + 1 + tid; i < K; i += kSolveThreads) A[i * LD + k] /= d;
+        __syncthreads();
+        // trailing update of the lower triangle: A[i][j] -= A[i][k] A[j][k] for k < j <= i
+        const int n = K - k - 1;
+        for (int e = tid; e < n * n; e += kSolveThreads) {
+            const int i = k + 1 + e / n, j = k + 1 + e % n;
+            if (j <= i) A[i * LD + j] -= A[i * LD + k] * A[j * LD + k];
+        }
+        __syncthreads();
+    }
+    // L^-1 column by column (thread c owns column c), stored in the strict upper part + diagonal copy:
+    // we overwrite A's upper triangle U[c][i] (row c, col i >= c) with Linv[i][c].
+    for (int c = tid; c < K; c += kSolveThreads) {
+        // forward substitution L x = e_c ; x_i = 0 for i < c
+        double* x = A + (size_t)c * LD;  // row c, entries c..K-1 of the UPPER triangle hold x_c..x_{K-1}
+        // careful: A[c][c] holds L[c][c]; compute x_c first into a register and write it last
+        const double xc = 1.0 / A[c * LD + c];
+        for (int i = c + 1; i < K; ++i) {
+            double s = A[i * LD + c] * xc;  // L[i][c] * x_c
+            for (int j = c + 1; j < i; ++j) s += A[i * LD + j] * x[j];   // L[i][j] * x_j (x_j in row c, col j)
+            x[i] = -s / A[i * LD + i];
+        }
+        mean[c] = xc;  // stash x_c (the diagonal still holds L[c][c] for the other threads)
+    }
+    __syncthreads();
+    for (int c = tid; c < K; c += kSolveThreads) A[c * LD + c] = mean[c];
+    __syncthreads();
+    // now Linv[i][c] = A[c][i] for i >= c.  V = Linv^T Linv: V[i][j] = sum_{k >= max(i,j)} Linv[k][i] Linv[k][j]
+    // write V (packed, float32) and keep a float64 copy of the lower triangle in A[i][j], i > j.
+    const size_t R = (size_t)(a.row_offset + row);
+    for (int e = tid; e < npk; e += kSolveThreads) {
+        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;
+        while (i * (i + 1) / 2 > e) --i;
+        const int j = e - i * (i + 1) / 2;  // j <= i
+        double s = 0.0;
+        for (int k = i; k < K; ++k) s += A[i * LD + k] * A[j * LD + k];
+        // stash: strictly-lower entries go to A[i][j]; the diagonal to rhs-sized buffer later
+        if (i != j) A[i * LD + j] = s; else mean[i] = s;  // mean[] reused as diag(V) (x_c already copied)
+    }
+    __syncthreads();
+    // m = V rhs / sigma2 (thread per row of V)
+    double mi = 0.0;
+    const bool own = tid < K;
+    for (int i = tid; i < K; i += kSolveThreads) {
+        double s = mean[i] * rhs[i];
+        for (int j = 0; j < K; ++j) {
+            if (j == i) continue;
+            const double vij = j < i ? A[i * LD + j] : A[j * LD + i];
+            s += vij * rhs[j];
+        }
+        mi = s / (double)a.sigma2;
+        a.m_self[R * a.ld + i] = (float)mi;
+        A[i * LD + K] = mi;  // column K of row i: the new mean (float64) for Q below
+    }
+    (void)own;
+    __syncthreads();
+    for (int e = tid; e < npk; e += kSolveThreads) {
+        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;
+        while (i * (i + 1) / 2 > e) --i;
+        const int j = e - i * (i + 1) / 2;
+        const double v = (i == j) ? mean[i] : A[i * LD + j];
+        a.V_self[R * a.ldq + e] = (float)v;
+        a.Q_self[R * a.ldq + e] = (float)(v + A[i * LD + K] * A[j * LD + K]);   // E[th th^T], :151 / :187
+    }
+}
+
+// Bias pass: one warp per row; 8 lanes per rating compute <m_self[row], m_oth[col]> (float64 accumulate).
+struct BiasArgs {
+    const int32_t *row_ptr, *col;
+    const float* val;
+    int32_t n_rows, row_offset, ld, nvec;
+    const float *m_self, *m_oth, *b_oth;
+    float* b_self;
+    float sigma2, eta_b2;
+};
+
+__global__ void __launch_bounds__(256) gauss_bias_kernel(const BiasArgs a) {
+    const int lane = threadIdx.x & 31, gl = lane & 7, grp = lane >> 3;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= a.n_rows) return;
+    const int row = (int)wid;
+    const int p0 = a.row_ptr[row], p1 = a.row_ptr[row + 1];
+    if (p0 == p1) return;  // gaussian_mf_cavi_bias.py:208-209
+    const size_t R = (size_t)(a.row_offset + row);
+    const float* own = a.m_self + R * a.ld;
+    double acc = 0.0;
+    for (int base = p0; base < p1; base += 4) {
+        const int p = base + grp;
+        const bool ok = p < p1;
+        const int c = ok ? __ldg(a.col + p) : 0;
+        double d = 0.0;
+        if (ok) {
+            const float* oth = a.m_oth + (size_t)c * a.ld;
+            for (int idx = gl; idx < a.nvec; idx += 8) {
+                const float4 x = ldg_f4(own + idx * 4), y = ldg_f4(oth + idx * 4);
+                d += (double)x.x * y.x + (double)x.y * y.y + (double)x.z * y.z + (double)x.w * y.w;
+            }
+        }
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        if (ok && gl == 0) acc += (double)__ldg(a.val + p) - (double)__ldg(a.b_oth + c) - d;
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    if (lane == 0) {
+        const double prec = 1.0 / (double)a.eta_b2 + (double)(p1 - p0) / (double)a.sigma2;   // :226
+        a.b_self[R] = (float)((1.0 / prec) / (double)a.sigma2 * acc);                          // :230
+    }
+}
+
+}  // namespace pmf
+
+using namespace pmf;
+
+extern "C" {
+
+int pmf_gauss_packed_stride(int K) { return K <= 0 ? 0 : ((K * (K + 1) / 2 + 7) / 8) * 8; }
+
+int64_t pmf_gauss_workspace_bytes(const pmf_csr* csr, int32_t K) {
+    if (!csr || K <= 0) return -1;
+    const CsrView c = csr_view(csr);
+    const int64_t w = (int64_t)pmf_gauss_packed_stride(K) + pmf_row_stride(K);
+    const int64_t b = (int64_t)c.n_seg * w * (int64_t)sizeof(float);
+    return b > 0 ? b : 16;
+}
+
+int pmf_gauss_factor_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_Q_oth,
+                          const float* d_b_oth, float* d_m_self, float* d_V_self, float* d_Q_self,
+                          const float* d_b_self, float sigma2, float eta2, void* d_workspace, void* stream) {
+    PMF_REQUIRE(csr != nullptr, "csr is NULL");
+    PMF_REQUIRE(K >= 1 && K <= 96, "K=%d outside [1, 96] for the Gaussian model", K);
+    PMF_REQUIRE(d_m_oth && d_Q_oth && d_m_self && d_V_self && d_Q_self && d_workspace, "NULL table");
+    PMF_REQUIRE((d_b_oth == nullptr) == (d_b_self == nullptr), "bias vectors go together");
+    PMF_REQUIRE(sigma2 > 0.f && eta2 > 0.f, "variances must be positive");
+    const CsrView c = csr_view(csr);
+    GaussArgs a;
+    a.seg_row = c.seg_row; a.seg_start = c.seg_start; a.seg_order = c.seg_order; a.row_ptr = c.row_ptr;
+    a.row_seg = c.row_seg; a.col = c.col; a.val = c.val;
+    a.n_seg = c.n_seg; a.n_rows = c.n_rows; a.seg_len = c.seg_len; a.row_offset = c.row_offset;
+    a.K = K; a.ld = pmf_row_stride(K); a.ldq = pmf_gauss_packed_stride(K); a.nq4 = a.ldq / 4; a.nm4 = a.ld / 4;
+    a.m_oth = d_m_oth; a.Q_oth = d_Q_oth; a.b_oth = d_b_oth; a.b_self = d_b_self;
+    a.m_self = d_m_self; a.V_self = d_V_self; a.Q_self = d_Q_self;
+    a.sigma2 = sigma2; a.eta2 = eta2; a.scratch = (float*)d_workspace;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c.n_seg > 0) {
+        const int nslots = a.nq4 + a.nm4;
+        // threads per segment: a multiple of 32 covering the slots with at most 4 per thread
+        int V = 1;
+        while (V < 4 && (nslots + V - 1) / V > 256) V *= 2;
+        int T = (((nslots + V - 1) / V) + 31) / 32 * 32;
+        if (T > 1024) { set_error("K=%d needs %d slots: too wide", K, nslots); return PMF_EUNSUPPORTED; }
+        if (V == 1) gauss_accumulate_kernel<1><<<c.n_seg, T, 0, s>>>(a);
+        else if (V == 2) gauss_accumulate_kernel<2><<<c.n_seg, T, 0, s>>>(a);
+        else gauss_accumulate_kernel<4><<<c.n_seg, T, 0, s>>>(a);
+        PMF_LAUNCH_CHECK();
+    }
+    if (c.n_rows > 0) {
+        const size_t smem = ((size_t)K * (K + 1) + 2 * (size_t)K) * sizeof(double);
+        if (smem > 48 * 1024)
+            PMF_CUDA(cudaFuncSetAttribute(gauss_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gauss_solve_kernel<<<c.n_rows, kSolveThreads, smem, s>>>(a);
+        PMF_LAUNCH_CHECK();
+    }
+    return PMF_OK;
+}
+
+int pmf_gauss_bias_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_m_self,
+                        const float* d_b_oth, float* d_b_self, float sigma2, float eta_b2, void* stream) {
+    PMF_REQUIRE(csr != nullptr, "csr is NULL");
+    PMF_REQUIRE(K >= 1, "K must be positive");
+    PMF_REQUIRE(d_m_oth && d_m_self && d_b_oth && d_b_self, "NULL table");
+    PMF_REQUIRE(sigma2 > 0.f && eta_b2 > 0.f, "variances must be positive");
+    const CsrView c = csr_view(csr);
+    BiasArgs a;
+    a.row_ptr = c.row_ptr; a.col = c.col; a.val = c.val; a.n_rows = c.n_rows; a.row_offset = c.row_offset;
+    a.ld = pmf_row_stride(K); a.nvec = a.ld / 4;
+    a.m_self = d_m_self; a.m_oth = d_m_oth; a.b_oth = d_b_oth; a.b_self = d_b_self;
+    a.sigma2 = sigma2; a.eta_b2 = eta_b2;
+    if (c.n_rows > 0) {
+        gauss_bias_kernel<<<(unsigned)cdiv((int64_t)c.n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(a);
+        PMF_LAUNCH_CHECK();
+    }
+    return PMF_OK;
+}
+
+}  // extern "C"
