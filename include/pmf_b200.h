@@ -149,6 +149,31 @@ int pmf_gauss_factor_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, c
 int pmf_gauss_bias_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_m_self,
                         const float* d_b_oth, float* d_b_self, float sigma2, float eta_b2, void* stream);
 
+/* ---- a6/a7: gradient-based HPF (HPF_PyTorch) ----------------------------------------------
+ * Parameters keep the reference's shapes (hpf_pytorch.py:39-48): theta_raw (N,K), beta_raw (M,K) row-major
+ * with row stride K, xi_raw (N), eta_raw (M), all float32 and unconstrained (softplus applied inside).
+ *
+ * pmf_hpf_map_loss_grad replaces HPF_PyTorch.loss (hpf_pytorch.py:71-184) AND its autograd backward:
+ * adds the batch loss (sum, not mean) to *d_loss (float64) and ACCUMULATES d loss / d raw-parameter into the
+ * dense gradient tensors (caller zero-fills them), summing over duplicate ids in the batch.  Ids are int64
+ * (id_bytes = 8, what the reference's LongTensors hold) or int32.  *d_bad is set to 1 if an id is out of
+ * range (torch would raise IndexError).
+ * pmf_adam_dense_step replaces torch.optim.Adam's update of one tensor (compare_models.py:288,312; defaults,
+ * no weight decay / amsgrad); step_size = lr/(1-beta1^t), bias_correction2_sqrt = sqrt(1-beta2^t).
+ * pmf_hpf_map_predict replaces forward/predict (hpf_pytorch.py:66-69, :186-195); float32 output. */
+int pmf_hpf_map_loss_grad(const void* d_users, const void* d_items, int32_t id_bytes, const float* d_ratings,
+                          int64_t B, const float* d_theta_raw, const float* d_beta_raw, const float* d_xi_raw,
+                          const float* d_eta_raw, const float* d_user_scale, const float* d_item_scale, int32_t N,
+                          int32_t M, int32_t K, float a, float a_prime, float b_prime, float c, float c_prime,
+                          float d_prime, float* d_g_theta, float* d_g_beta, float* d_g_xi, float* d_g_eta,
+                          double* d_loss, int32_t* d_bad, void* stream);
+int pmf_adam_dense_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
+                        float beta1, float beta2, float eps, float step_size, float bias_correction2_sqrt,
+                        void* stream);
+int pmf_hpf_map_predict(const void* d_users, const void* d_items, int32_t id_bytes, int64_t n,
+                        const float* d_theta_raw, const float* d_beta_raw, int32_t N, int32_t M, int32_t K,
+                        float* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,198 @@
+"""Drop-in for the reference's ``src.models.hpf_pytorch`` (hpf_pytorch.py:9-195): gradient-based (MAP)
+hierarchical Poisson factorisation as a ``torch.nn.Module``.
+
+The scripts that drive it (compare_models.py:287-313, train_hpf_pytorch_full.py:76-108,
+tune_all_models.py:238-266) build ``torch.optim.Adam(model.parameters())``, feed CPU ``LongTensor`` /
+``FloatTensor`` mini-batches and call ``loss(...).backward()``; they never call ``.to(device)``.  This
+class therefore owns CUDA parameters internally, accepts CPU batches, and implements ``loss`` as a
+``torch.autograd.Function`` whose forward launches ONE fused kernel (``pmf_hpf_map_loss_grad``) that
+computes the loss and the analytic gradient of every term on the touched rows only; ``backward`` hands
+those gradients to autograd, so the scripts' own optimiser loop runs unchanged.
+
+``fit_epochs`` is the loader-free fast path: it replays torch's DataLoader shuffle stream
+(bit-identical permutations) and steps with the fused ``pmf_adam_dense_step`` kernel.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _cabi
+
+
+@dataclass
+class HPF_PyTorch_Config:
+    n_factors: int = 20
+    a: float = 0.3
+    a_prime: float = 1.0
+    b_prime: float = 1.0
+    c: float = 0.3
+    c_prime: float = 1.0
+    d_prime: float = 1.0
+    lr: float = 0.001
+    batch_size: int = 1024
+    epochs: int = 20
+    device: str = "cpu"        # kept for config round-trips; the engine always runs on the GPU
+    verbose: bool = True
+
+
+def _loss_grad(mod, users, items, ratings, grads, loss_acc):
+    cfg = mod.config
+    id_bytes = 8 if users.dtype == torch.int64 else 4
+    with torch.cuda.device(mod.theta_uncons.device):
+        _cabi.call("pmf_hpf_map_loss_grad", users.data_ptr(), items.data_ptr(), id_bytes, ratings.data_ptr(),
+                   users.numel(), mod.theta_uncons.data_ptr(), mod.beta_uncons.data_ptr(), mod.xi_uncons.data_ptr(),
+                   mod.eta_uncons.data_ptr(), mod.user_scale.data_ptr(), mod.item_scale.data_ptr(), mod.n_users,
+                   mod.n_items, mod.K, cfg.a, cfg.a_prime, cfg.b_prime, cfg.c, cfg.c_prime, cfg.d_prime,
+                   grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(), grads[3].data_ptr(),
+                   loss_acc.data_ptr(), mod._bad.data_ptr(), _cabi.stream_ptr())
+
+
+class _FusedLoss(torch.autograd.Function):
+    """loss = HPF_PyTorch.loss(batch); gradients come from the same kernel launch as the value."""
+
+    @staticmethod
+    def forward(ctx, theta, beta, xi, eta, mod, users, items, ratings):
+        grads = [torch.zeros_like(p) for p in (theta, beta, xi, eta)]
+        acc = torch.zeros((), dtype=torch.float64, device=theta.device)
+        _loss_grad(mod, users, items, ratings, grads, acc)
+        ctx.grads = grads
+        return acc.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, gout):
+        g = ctx.grads
+        ctx.grads = None
+        return g[0].mul_(gout), g[1].mul_(gout), g[2].mul_(gout), g[3].mul_(gout), None, None, None, None
+
+
+class HPF_PyTorch(nn.Module):
+    def __init__(self, n_users, n_items, user_counts, item_counts, config: HPF_PyTorch_Config, device=None):
+        super().__init__()
+        _cabi.require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.config = config
+        self.n_users = int(n_users)
+        self.n_items = int(n_items)
+        self.K = int(config.n_factors)
+        # Buffers for scaling (hpf_pytorch.py:34-35), computed on the host exactly as the reference does
+        self.register_buffer("user_scale", (1.0 / (torch.tensor(user_counts, dtype=torch.float32) + 1e-6)).to(dev))
+        self.register_buffer("item_scale", (1.0 / (torch.tensor(item_counts, dtype=torch.float32) + 1e-6)).to(dev))
+        # Same draws from the global CPU generator, same order (theta, beta, xi, eta; hpf_pytorch.py:39-48)
+        self.theta_uncons = nn.Parameter((torch.randn(self.n_users, self.K) * 0.1).to(dev))
+        self.beta_uncons = nn.Parameter((torch.randn(self.n_items, self.K) * 0.1).to(dev))
+        self.xi_uncons = nn.Parameter((torch.randn(self.n_users) * 0.1).to(dev))
+        self.eta_uncons = nn.Parameter((torch.randn(self.n_items) * 0.1).to(dev))
+        self.register_buffer("_bad", torch.zeros(1, dtype=torch.int32, device=dev), persistent=False)
+        self._adam = None
+
+    # -- constrained views (outputs only; the training kernels apply softplus on touched rows) -------
+    @property
+    def theta(self):
+        return F.softplus(self.theta_uncons)
+
+    @property
+    def beta(self):
+        return F.softplus(self.beta_uncons)
+
+    @property
+    def xi(self):
+        return F.softplus(self.xi_uncons)
+
+    @property
+    def eta(self):
+        return F.softplus(self.eta_uncons)
+
+    def _ids(self, t):
+        if isinstance(t, np.ndarray):
+            t = torch.from_numpy(np.ascontiguousarray(t))
+        if t.dtype not in (torch.int64, torch.int32):
+            t = t.long()
+        return t.to(self.theta_uncons.device, non_blocking=True).contiguous()
+
+    def forward(self, user_ids, item_ids):
+        u, i = self._ids(user_ids), self._ids(item_ids)
+        out = torch.empty(u.numel(), dtype=torch.float32, device=u.device)
+        with torch.cuda.device(u.device):
+            _cabi.call("pmf_hpf_map_predict", u.data_ptr(), i.data_ptr(), 8 if u.dtype == torch.int64 else 4, u.numel(),
+                       self.theta_uncons.data_ptr(), self.beta_uncons.data_ptr(), self.n_users, self.n_items, self.K,
+                       out.data_ptr(), _cabi.stream_ptr())
+        return out
+
+    def loss(self, user_ids, item_ids, ratings):
+        """Negative log joint of the mini-batch (sum over the batch), differentiable w.r.t. the parameters."""
+        u, i = self._ids(user_ids), self._ids(item_ids)
+        if u.dtype != i.dtype:
+            u, i = u.long(), i.long()
+        r = torch.as_tensor(ratings).to(torch.float32).to(u.device, non_blocking=True).contiguous()
+        return _FusedLoss.apply(self.theta_uncons, self.beta_uncons, self.xi_uncons, self.eta_uncons, self, u, i, r)
+
+    def predict(self, user_ids, item_ids):
+        with torch.no_grad():
+            preds = self.forward(user_ids, item_ids)
+        return preds.cpu().numpy()
+
+    def check_ids(self):
+        """Raise like torch indexing would if any batch so far carried an out-of-range id (one D2H)."""
+        if int(self._bad.item()) != 0:
+            raise IndexError("index out of range in HPF_PyTorch batch")
+
+    # -- loader-free training ------------------------------------------------------------------------
+    def fit_epochs(self, users, items, ratings, epochs=None, batch_size=4096, lr=None, shuffle=True, on_epoch=None):
+        """The scripts' loop (compare_models.py:299-313) without the DataLoader.
+
+        Per epoch the shuffle is torch's own: ``DataLoader.__iter__`` draws ``_base_seed`` then
+        ``RandomSampler`` draws its seed from the global CPU generator and calls
+        ``torch.randperm(n, generator=Generator().manual_seed(seed))`` -- replayed here bit for bit, so a
+        run under the same ``torch.manual_seed`` visits the same mini-batches as the reference loop.
+        Each step = one fused loss+gradient kernel and one fused dense Adam kernel per tensor.
+        Returns the list of epoch losses (sum of mini-batch losses, as the scripts print).
+        """
+        cfg = self.config
+        epochs = cfg.epochs if epochs is None else epochs
+        lr = cfg.lr if lr is None else lr
+        dev = self.theta_uncons.device
+        u_all, i_all = self._ids(users), self._ids(items)
+        r_all = torch.as_tensor(np.asarray(ratings, dtype=np.float32)).to(dev)
+        n = u_all.numel()
+        params = [self.theta_uncons, self.beta_uncons, self.xi_uncons, self.eta_uncons]
+        if self._adam is None:
+            self._adam = {"step": 0, "m": [torch.zeros_like(p) for p in params], "v": [torch.zeros_like(p) for p in params]}
+        st = self._adam
+        grads = [torch.zeros_like(p) for p in params]
+        beta1, beta2, eps = 0.9, 0.999, 1e-8
+        losses = []
+        with torch.cuda.device(dev), torch.no_grad():
+            for ep in range(epochs):
+                if shuffle:
+                    _base_seed = torch.empty((), dtype=torch.int64).random_()          # dataloader.py _BaseDataLoaderIter
+                    seed = int(torch.empty((), dtype=torch.int64).random_().item())    # sampler.py RandomSampler.__iter__
+                    gen = torch.Generator()
+                    gen.manual_seed(seed)
+                    perm = torch.randperm(n, generator=gen).to(dev)
+                    u_ep, i_ep, r_ep = u_all[perm], i_all[perm], r_all[perm]
+                else:
+                    u_ep, i_ep, r_ep = u_all, i_all, r_all
+                acc = torch.zeros((), dtype=torch.float64, device=dev)
+                for s in range(0, n, batch_size):
+                    e = min(s + batch_size, n)
+                    for g in grads:
+                        g.zero_()
+                    _loss_grad(self, u_ep[s:e], i_ep[s:e], r_ep[s:e], grads, acc)
+                    st["step"] += 1
+                    t = st["step"]
+                    step_size = lr / (1.0 - beta1 ** t)
+                    bc2_sqrt = math.sqrt(1.0 - beta2 ** t)
+                    for p, g, m, v in zip(params, grads, st["m"], st["v"]):
+                        _cabi.call("pmf_adam_dense_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
+                                   beta1, beta2, eps, step_size, bc2_sqrt, _cabi.stream_ptr())
+                losses.append(float(acc.item()))
+                if on_epoch is not None:
+                    on_epoch(ep, losses[-1])
+        self.check_ids()
+        return losses
