@@ -83,6 +83,7 @@ def make_model(w, steps, device=None, shard=None, seg_len=None):
         m = HPF_CAVI(HPF_CAVI_Config(n_factors=w.n_factors, max_iter=steps, tol=None, random_state=42, verbose=False,
                                      **HPF_HP), device=device, shard=shard, **kw)
     m.n_users, m.n_items = w.n_users, w.n_items
+    m._auto_close = False            # keep the (peer-mapped) engine alive for the device-resident timing
     return m
 
 
@@ -240,6 +241,7 @@ def main():
     ap.add_argument("--seg-len", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default=None, choices=["p2p", "nccl"], help="multi-GPU row exchange (default p2p)")
     ap.add_argument("--tune", default="", help="comma list key=value passed to pmf_tune (experiments)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -250,6 +252,8 @@ def main():
     from prob_matrix_factorization_b200 import _cabi
     from prob_matrix_factorization_b200.parallel import init_process_group
 
+    if args.exchange:
+        os.environ["PMF_EXCHANGE"] = args.exchange
     rank, world, local = init_process_group()
     if world != args.gpus:
         log(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
@@ -366,6 +370,10 @@ def main():
             "config": {"workload": f"{w.name}: {w.model} K={w.n_factors}, {w.n_users} users x {w.n_items} items x "
                                    f"{w.nnz} ratings (BASELINE.json configs[{int(w.name[1]) - 1}])",
                        "sharding": "ratings by nonzero (row-aligned), factors replicated" if world > 1 else "single GPU",
+                       "row_exchange": {"p2p": "fused into the pass kernel: P2P stores to peer replicas over NVLink + "
+                                               "1-element NCCL all-reduce as inter-pass barrier",
+                                        "nccl": "NCCL all-gather of owned rows after each pass",
+                                        "none": None}[eng.exchange],
                        "l2": "working set 2.9+ GB >> 126 MB L2; no flush needed",
                        "seg_len": eng.r.by_user.seg_len if eng.r.by_user is not None else None},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,

@@ -103,6 +103,23 @@ int pmf_gamma_pass(const pmf_csr* csr, int32_t K, int32_t ld,
                    float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior,
                    void* d_workspace, void* stream);
 
+/* Multi-GPU variant with the row exchange FUSED into the pass: every finished row of
+ * E_self (and hyper_mean) is also stored, by the kernel that computed it, into the other ranks' replicas
+ * through peer-mapped pointers (NVLink P2P stores), so the transfer overlaps the pass tile by tile and no
+ * separate all-gather is needed; callers barrier across ranks between passes.  h_peer_* are HOST arrays of
+ * n_peers (<= 7) device pointers obtained from pmf_ipc_open. */
+int pmf_gamma_pass_p2p(const pmf_csr* csr, int32_t K, int32_t ld,
+                       const float* d_E_oth, float* d_E_self, float* d_shp, float* d_rte,
+                       float shape_prior, float rate_prior, const float* d_rate_prior_vec,
+                       float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior,
+                       void* d_workspace, int32_t n_peers, void* const* h_peer_E_self,
+                       void* const* h_peer_hyper_mean, void* stream);
+/* Peer-mappable device memory (CUDA IPC): allocate + export a 64-byte handle / map a peer's handle. */
+int pmf_ipc_alloc(int64_t bytes, void** d_ptr, void* handle64);
+int pmf_ipc_open(const void* handle64, void** d_ptr);
+int pmf_ipc_close(void* d_ptr);
+int pmf_ipc_free(void* d_ptr);
+
 /* ---- a8-a10: predict and evaluation -------------------------------------------------
  * predict (poisson_mf_cavi.py:221-241, hpf_cavi.py:215-231, gaussian_mf_cavi_bias.py:291-316,
  * hpf_pytorch.py:66-69,186-195): pred = <F_user[u], F_item[i]> (+ b_user[u] + b_item[i]) for

@@ -54,6 +54,12 @@ _PROTOTYPES = {
     "pmf_gamma_pass_workspace_bytes": (C.c_int64, [VP, C.c_int32]),
     "pmf_gamma_pass": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP, VP, VP, C.c_float, C.c_float, VP,
                                  VP, VP, C.c_float, C.c_float, VP, VP]),
+    "pmf_gamma_pass_p2p": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP, VP, VP, C.c_float, C.c_float, VP,
+                                     VP, VP, C.c_float, C.c_float, VP, C.c_int32, C.POINTER(VP), C.POINTER(VP), VP]),
+    "pmf_ipc_alloc": (C.c_int, [C.c_int64, C.POINTER(VP), VP]),
+    "pmf_ipc_open": (C.c_int, [VP, C.POINTER(VP)]),
+    "pmf_ipc_close": (C.c_int, [VP]),
+    "pmf_ipc_free": (C.c_int, [VP]),
     "pmf_gauss_packed_stride": (C.c_int, [C.c_int]),
     "pmf_gauss_workspace_bytes": (C.c_int64, [VP, C.c_int32]),
     "pmf_gauss_factor_pass": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, VP, VP, C.c_float, C.c_float, VP, VP]),

@@ -6,12 +6,13 @@ libpmf_b200 kernel launched through ctypes on torch-owned device memory.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
 
 from . import _cabi
-from .parallel import RowExchange
+from .parallel import PeerTable, RowExchange
 from .ratings import DeviceRatings, as_id_array, to_device
 
 MAX_DEVICE_LABELS = 64
@@ -134,7 +135,7 @@ class GammaEngine:
     """
 
     def __init__(self, ratings: DeviceRatings, K, user_shape, item_shape, user_rate=None, item_rate=None,
-                 hyper=None, keep_params=True):
+                 hyper=None, keep_params=True, exchange=None):
         self.r = ratings
         self.dev = ratings.device
         self.K = int(K)
@@ -147,20 +148,40 @@ class GammaEngine:
         self.hyper = hyper
         self.keep_params = keep_params
         f = lambda rows: torch.zeros((rows, self.ld), dtype=torch.float32, device=self.dev)
-        self.E_theta, self.E_beta = f(self.N), f(self.M)
+        # multi-GPU row exchange: "p2p" = fused into the pass kernel over peer-mapped replicas (default),
+        # "nccl" = all-gather of owned rows after the pass
+        if exchange is None:
+            exchange = os.environ.get("PMF_EXCHANGE", "p2p")
+        self.exchange = exchange if ratings.world > 1 else "none"
+        self._peer = {}
+        if self.exchange == "p2p":
+            import torch.distributed as dist
+            for name, shape in (("E_theta", (self.N, self.ld)), ("E_beta", (self.M, self.ld))) + \
+                    ((("E_xi", (self.N,)), ("E_eta", (self.M,))) if hyper is not None else ()):
+                self._peer[name] = PeerTable(shape, self.dev)
+            self.E_theta, self.E_beta = self._peer["E_theta"].local, self._peer["E_beta"].local
+            self._token = torch.zeros(1, dtype=torch.float32, device=self.dev)
+            dist.barrier()
+        else:
+            self.E_theta, self.E_beta = f(self.N), f(self.M)
         self.shp_theta = f(self.N) if keep_params else None
         self.rte_theta = f(self.N) if keep_params else None
         self.shp_beta = f(self.M) if keep_params else None
         self.rte_beta = f(self.M) if keep_params else None
         if hyper is not None:
             v = lambda rows: torch.zeros(rows, dtype=torch.float32, device=self.dev)
-            self.rate_xi, self.E_xi, self.rate_eta, self.E_eta = v(self.N), v(self.N), v(self.M), v(self.M)
+            self.rate_xi, self.rate_eta = v(self.N), v(self.M)
+            if self.exchange == "p2p":
+                self.E_xi, self.E_eta = self._peer["E_xi"].local, self._peer["E_eta"].local
+            else:
+                self.E_xi, self.E_eta = v(self.N), v(self.M)
         else:
             self.rate_xi = self.E_xi = self.rate_eta = self.E_eta = None
         self.ws_user = ratings.by_user.workspace(self.ld) if ratings.by_user is not None else None
         self.ws_item = ratings.by_item.workspace(self.ld) if ratings.by_item is not None else None
         self.xu = RowExchange(ratings.user_bounds) if ratings.world > 1 else None
         self.xi_ = RowExchange(ratings.item_bounds) if ratings.world > 1 else None
+        self.n_peers = ratings.world - 1 if self.exchange == "p2p" else 0
         self.launches_per_sweep = sum(
             (1 if g.n_segments > 0 else 0) + (1 if g.n_multi_rows > 0 else 0)
             for g in (ratings.by_user, ratings.by_item) if g is not None)
@@ -187,34 +208,62 @@ class GammaEngine:
 
     # -- one pass ------------------------------------------------------------------------------
     def _pass(self, grouped, E_oth, E_self, shp, rte, shape_prior, rate_prior, rate_vec, hyper_rate, hyper_mean,
-              hyper_shape, hyper_rate_prior, ws):
+              hyper_shape, hyper_rate_prior, ws, peer_E=None, peer_hyper=None):
         if grouped is None:
             return
-        _cabi.call("pmf_gamma_pass", grouped.handle, self.K, self.ld, E_oth.data_ptr(), E_self.data_ptr(),
+        _cabi.call("pmf_gamma_pass_p2p", grouped.handle, self.K, self.ld, E_oth.data_ptr(), E_self.data_ptr(),
                    _cabi.ptr(shp), _cabi.ptr(rte), shape_prior, 0.0 if rate_prior is None else rate_prior,
                    _cabi.ptr(rate_vec), _cabi.ptr(hyper_rate), _cabi.ptr(hyper_mean), hyper_shape,
-                   hyper_rate_prior, _cabi.ptr(ws), _cabi.stream_ptr())
+                   hyper_rate_prior, _cabi.ptr(ws), self.n_peers if peer_E is not None else 0,
+                   peer_E.peer_array if peer_E is not None else None,
+                   peer_hyper.peer_array if peer_hyper is not None else None, _cabi.stream_ptr())
+
+    def _rank_barrier(self):
+        """All ranks' pass kernels (and their P2P stores into this replica) are complete after this."""
+        import torch.distributed as dist
+        dist.all_reduce(self._token)
 
     def user_pass(self):
         h = self.hyper
         self._pass(self.r.by_user, self.E_beta, self.E_theta, self.shp_theta, self.rte_theta, self.user_shape,
                    self.user_rate, self.E_xi, self.rate_xi, self.E_xi,
-                   h["user_shape"] if h else 0.0, h["user_rate_prior"] if h else 0.0, self.ws_user)
-        if self.xu is not None:
+                   h["user_shape"] if h else 0.0, h["user_rate_prior"] if h else 0.0, self.ws_user,
+                   self._peer.get("E_theta"), self._peer.get("E_xi"))
+        if self.exchange == "p2p":
+            self._rank_barrier()
+        elif self.xu is not None:
             self.xu.gather(*([self.E_theta] + ([self.E_xi] if h else [])))
 
     def item_pass(self):
         h = self.hyper
         self._pass(self.r.by_item, self.E_theta, self.E_beta, self.shp_beta, self.rte_beta, self.item_shape,
                    self.item_rate, self.E_eta, self.rate_eta, self.E_eta,
-                   h["item_shape"] if h else 0.0, h["item_rate_prior"] if h else 0.0, self.ws_item)
-        if self.xi_ is not None:
+                   h["item_shape"] if h else 0.0, h["item_rate_prior"] if h else 0.0, self.ws_item,
+                   self._peer.get("E_beta"), self._peer.get("E_eta"))
+        if self.exchange == "p2p":
+            self._rank_barrier()
+        elif self.xi_ is not None:
             self.xi_.gather(*([self.E_beta] + ([self.E_eta] if h else [])))
 
     def sweep(self):
         with torch.cuda.device(self.dev):
             self.user_pass()
             self.item_pass()
+
+    def close(self):
+        """Unmap / free peer-shared tables (multi-GPU p2p exchange).  Call on every rank."""
+        if self._peer:
+            import torch.distributed as dist
+            keep = {k: getattr(self, k).clone() for k in self._peer}     # state stays readable after close
+            torch.cuda.synchronize(self.dev)
+            dist.barrier()
+            for t in self._peer.values():
+                t.close()
+            self._peer = {}
+            for k, v in keep.items():
+                setattr(self, k, v)
+            self.exchange = "closed"
+            self.n_peers = 0
 
     def sync_params(self):
         """Multi-GPU: make the Gamma shape/rate tables (only needed as outputs) complete on every rank."""

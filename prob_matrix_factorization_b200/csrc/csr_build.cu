@@ -417,6 +417,41 @@ int pmf_copy_to_host(void* h_dst, const void* d_src, int64_t bytes, void* stream
     return PMF_OK;
 }
 
+// ---- peer-mapped device memory (CUDA IPC) for the fused row exchange -----------------------------------
+int pmf_ipc_alloc(int64_t bytes, void** d_ptr, void* handle64) {
+    PMF_REQUIRE(bytes > 0 && d_ptr && handle64, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    PMF_CUDA(cudaMalloc(d_ptr, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*d_ptr);
+        *d_ptr = nullptr;
+        set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+        return PMF_ECUDA;
+    }
+    memcpy(handle64, &h, 64);
+    return PMF_OK;
+}
+
+int pmf_ipc_open(const void* handle64, void** d_ptr) {
+    PMF_REQUIRE(handle64 && d_ptr, "bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    PMF_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PMF_OK;
+}
+
+int pmf_ipc_close(void* d_ptr) {
+    if (d_ptr) PMF_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return PMF_OK;
+}
+
+int pmf_ipc_free(void* d_ptr) {
+    if (d_ptr) PMF_CUDA(cudaFree(d_ptr));
+    return PMF_OK;
+}
+
 int pmf_row_stride(int K) { return K <= 0 ? 0 : ((K + 7) / 8) * 8; }
 
 int pmf_csr_free(pmf_csr* c) {

@@ -21,6 +21,8 @@
 
 namespace pmf {
 
+constexpr int kMaxPeers = 7;   // 8 GPUs per NVSwitch domain
+
 struct GammaArgs {
     const int32_t *seg_row, *seg_start, *seg_partial, *seg_order, *row_ptr, *col;
     const float* val;
@@ -36,6 +38,11 @@ struct GammaArgs {
     float* hyper_mean;
     float hyper_shape, hyper_rate_prior;
     float* partial;  // [n_partial][2*ld]: sum (x/rate) E_oth | sum E_oth
+    // fused row exchange (multi-GPU): the other ranks' replicas of E_self / hyper_mean, mapped over NVLink.
+    // Every finished row is stored to all replicas by the same kernel that computed it.
+    int32_t n_peers;
+    float* peer_E[kMaxPeers];
+    float* peer_hyper_mean[kMaxPeers];
 };
 
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -80,6 +87,8 @@ __device__ __forceinline__ void gamma_row_update(const GammaArgs& a, int R, int 
             if (a.shp) *reinterpret_cast<float4*>(a.shp + rowoff + k0) = s;
             if (a.rte) *reinterpret_cast<float4*>(a.rte + rowoff + k0) = r;
             *reinterpret_cast<float4*>(a.E_self + rowoff + k0) = e;
+            for (int pr = 0; pr < a.n_peers; ++pr)   // P2P stores: 16*G contiguous bytes per group and peer
+                *reinterpret_cast<float4*>(a.peer_E[pr] + rowoff + k0) = e;
             esum += (e.x + e.y) + (e.z + e.w);
         }
     }
@@ -87,8 +96,10 @@ __device__ __forceinline__ void gamma_row_update(const GammaArgs& a, int R, int 
         esum = group_sum<G>(esum, gmask);
         if (gl == 0) {
             const float hr = a.hyper_rate_prior + esum;   // hpf_cavi.py:158 / :192
+            const float hm = a.hyper_shape / hr;          // hpf_cavi.py:94-95
             a.hyper_rate[R] = hr;
-            a.hyper_mean[R] = a.hyper_shape / hr;          // hpf_cavi.py:94-95
+            a.hyper_mean[R] = hm;
+            for (int pr = 0; pr < a.n_peers; ++pr) a.peer_hyper_mean[pr][R] = hm;
         }
     }
 }
@@ -275,6 +286,16 @@ int pmf_gamma_pass(const pmf_csr* csr, int32_t K, int32_t ld, const float* d_E_o
                    float* d_rte, float shape_prior, float rate_prior, const float* d_rate_prior_vec,
                    float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior,
                    void* d_workspace, void* stream) {
+    return pmf_gamma_pass_p2p(csr, K, ld, d_E_oth, d_E_self, d_shp, d_rte, shape_prior, rate_prior, d_rate_prior_vec,
+                              d_hyper_rate, d_hyper_mean, hyper_shape, hyper_rate_prior, d_workspace, 0, nullptr,
+                              nullptr, stream);
+}
+
+int pmf_gamma_pass_p2p(const pmf_csr* csr, int32_t K, int32_t ld, const float* d_E_oth, float* d_E_self, float* d_shp,
+                       float* d_rte, float shape_prior, float rate_prior, const float* d_rate_prior_vec,
+                       float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior,
+                       void* d_workspace, int32_t n_peers, void* const* h_peer_E_self,
+                       void* const* h_peer_hyper_mean, void* stream) {
     PMF_REQUIRE(csr != nullptr, "csr is NULL");
     PMF_REQUIRE(K >= 1 && ld >= K && ld % 8 == 0 && ld <= 256, "need 1 <= K <= ld <= 256 and ld %% 8 == 0 (K=%d ld=%d)", K, ld);
     PMF_REQUIRE(d_E_oth && d_E_self, "factor tables are NULL");
@@ -291,6 +312,14 @@ int pmf_gamma_pass(const pmf_csr* csr, int32_t K, int32_t ld, const float* d_E_o
     a.shape_prior = shape_prior; a.rate_prior = rate_prior; a.rate_prior_vec = d_rate_prior_vec;
     a.hyper_rate = d_hyper_rate; a.hyper_mean = d_hyper_mean; a.hyper_shape = hyper_shape;
     a.hyper_rate_prior = hyper_rate_prior; a.partial = (float*)d_workspace;
+    PMF_REQUIRE(n_peers >= 0 && n_peers <= kMaxPeers, "n_peers=%d outside [0, %d]", n_peers, kMaxPeers);
+    PMF_REQUIRE(n_peers == 0 || h_peer_E_self != nullptr, "peer table pointers are NULL");
+    PMF_REQUIRE(n_peers == 0 || d_hyper_rate == nullptr || h_peer_hyper_mean != nullptr, "peer hyper pointers are NULL");
+    a.n_peers = n_peers;
+    for (int pr = 0; pr < kMaxPeers; ++pr) {
+        a.peer_E[pr] = pr < n_peers ? (float*)h_peer_E_self[pr] : nullptr;
+        a.peer_hyper_mean[pr] = (pr < n_peers && h_peer_hyper_mean) ? (float*)h_peer_hyper_mean[pr] : nullptr;
+    }
     const bool hyper = d_hyper_rate != nullptr;
     cudaStream_t s = (cudaStream_t)stream;
     const int nv = a.nvec;

@@ -57,6 +57,7 @@ class HPF_CAVI(_DeviceBacked):
         self._device = device
         self._shard = shard
         self._seg_len = seg_len
+        self._auto_close = True
         self.n_iter_ = 0
         self.val_rmse_history_ = []
         self._init = None
@@ -115,6 +116,8 @@ class HPF_CAVI(_DeviceBacked):
         if init is None:
             init = self._initial_state()
         self.gamma_a_xi, self.gamma_a_eta = init["gamma_a_xi"], init["gamma_a_eta"]
+        if self._engine is not None:
+            self._engine.close()          # collective on multi-GPU runs: every rank re-fits together
         dr = DeviceRatings(user_ids, item_ids, ratings, self.n_users, self.n_items, self._device,
                            seg_len=self._seg_len, shard=self._shard)
         hyper = {"user_shape": float(init["gamma_a_xi"]), "user_rate_prior": float(cfg.b_prime),
@@ -151,6 +154,8 @@ class HPF_CAVI(_DeviceBacked):
                         break
                 prev_val_rmse = val_rmse
         eng.sync_params()
+        if self._auto_close:
+            eng.close()                   # peer-mapped tables (multi-GPU) become ordinary device tensors
         if self.n_iter_ > 0:
             self._init = None
         self._invalidate()

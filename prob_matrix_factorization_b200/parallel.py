@@ -85,3 +85,62 @@ class RowExchange:
             for g, v in enumerate(views):
                 if v.numel() > 0:
                     dist.broadcast(v, src=dist.get_global_rank(self.group, g) if self.group else g, group=self.group)
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ carrier so torch can view library-allocated device memory."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerTable:
+    """A replicated float32 table whose copies on the other ranks are mapped into this process (CUDA IPC).
+
+    ``local`` is a torch view of this rank's copy; ``peer_ptrs`` are the other ranks' copies as raw device
+    pointers reachable over NVLink (P2P loads/stores).  Used by the fused pass+exchange kernel
+    (``pmf_gamma_pass_p2p``): each rank stores the rows it owns straight into every replica.
+    """
+
+    def __init__(self, shape, device, group=None):
+        import ctypes as C
+
+        from . import _cabi
+        self.device = torch.device(device)
+        self.shape = tuple(int(s) for s in shape)
+        nbytes = 4 * int(np.prod(self.shape))
+        self._ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            _cabi.call("pmf_ipc_alloc", max(nbytes, 64), C.byref(self._ptr), handle)
+            self.local = torch.as_tensor(_CudaArray(self._ptr.value, self.shape), device=self.device)
+            self.local.zero_()
+        world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self._opened = []
+        self.peer_ptrs = []
+        with torch.cuda.device(self.device):
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    continue
+                p = C.c_void_p()
+                _cabi.call("pmf_ipc_open", C.create_string_buffer(h, 64), C.byref(p))
+                self._opened.append(p)
+                self.peer_ptrs.append(p.value)
+        self.peer_array = (C.c_void_p * max(1, len(self.peer_ptrs)))(*self.peer_ptrs)
+
+    def close(self):
+        from . import _cabi
+        lib = _cabi.load()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for p in self._opened:
+                lib.pmf_ipc_close(p)
+            self._opened = []
+            if self._ptr is not None and self._ptr.value:
+                self.local = None
+                lib.pmf_ipc_free(self._ptr)
+                self._ptr = None

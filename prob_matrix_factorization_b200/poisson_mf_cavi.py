@@ -90,6 +90,7 @@ class PoissonMFCAVI(_DeviceBacked):
         self._device = device
         self._shard = shard
         self._seg_len = seg_len
+        self._auto_close = True
         self.n_iter_ = 0
         self.val_rmse_history_ = []
 
@@ -149,6 +150,8 @@ class PoissonMFCAVI(_DeviceBacked):
             self.n_users, self.n_items = int(np.max(user_ids)) + 1, int(np.max(item_ids)) + 1
         if init is None:
             init = self._initial_state()
+        if self._engine is not None:
+            self._engine.close()          # collective on multi-GPU runs: every rank re-fits together
         dr = DeviceRatings(user_ids, item_ids, ratings, self.n_users, self.n_items, self._device,
                            seg_len=self._seg_len, shard=self._shard)
         eng = GammaEngine(dr, cfg.n_factors, cfg.a0, cfg.a0, cfg.b0, cfg.b0)
@@ -183,6 +186,8 @@ class PoissonMFCAVI(_DeviceBacked):
                         break
                 prev_val_rmse = val_rmse
         eng.sync_params()
+        if self._auto_close:
+            eng.close()                   # peer-mapped tables (multi-GPU) become ordinary device tensors
         self._invalidate()
         if self.n_iter_ == 0:
             self._host.update({"a_theta": init["a_theta"], "a_beta": init["a_beta"]})

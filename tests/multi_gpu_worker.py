@@ -22,6 +22,7 @@ def rel_max(a, b):
 
 
 def main():
+    os.environ["PMF_EXCHANGE"] = sys.argv[1] if len(sys.argv) > 1 else "p2p"
     rank, world, local = init_process_group()
     dev = torch.device("cuda", local)
     N, M, nnz, K, T = 30_000, 12_000, 400_000, 24, 10
@@ -38,6 +39,7 @@ def main():
     for k in ("gamma_a_theta", "gamma_b_theta", "gamma_a_beta", "gamma_b_beta", "gamma_b_xi", "gamma_b_eta",
               "E_theta", "E_beta", "E_xi", "E_eta"):
         worst = max(worst, rel_max(getattr(m, k), ref[k]))
+    assert m._engine.exchange == "closed" if os.environ["PMF_EXCHANGE"] == "p2p" else m._engine.exchange == "nccl"
     # every rank must hold the same replicated tables bit for bit
     h = torch.stack([m._engine.E_theta.double().sum(), m._engine.E_beta.double().sum()])
     hs = [torch.zeros_like(h) for _ in range(world)]
