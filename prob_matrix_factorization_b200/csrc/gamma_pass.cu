@@ -40,6 +40,10 @@ struct GammaArgs {
     float* partial;  // [n_partial][2*ld]: sum (x/rate) E_oth | sum E_oth
     // fused row exchange (multi-GPU): the other ranks' replicas of E_self / hyper_mean, mapped over NVLink.
     // Every finished row is stored to all replicas by the same kernel that computed it.
+    // block -> chunk of the longest-first segment list: chunk = (blockIdx.x * block_stride) % gridDim.x with
+    // gcd(block_stride, gridDim.x) = 1.  stride 1 = longest first; a large stride interleaves long and short
+    // segments over the launch so that row completions (= P2P row stores) are spread over the whole kernel.
+    uint32_t block_stride;
     int32_t n_peers;
     float* peer_E[kMaxPeers];
     float* peer_hyper_mean[kMaxPeers];
@@ -110,7 +114,8 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
     static_assert(G % U == 0, "U must divide G");
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);
-    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const uint32_t chunk = (uint32_t)(((uint64_t)blockIdx.x * a.block_stride) % gridDim.x);
+    const int64_t gid = ((int64_t)chunk * blockDim.x + threadIdx.x) / G;
     const bool has = gid < a.n_seg;
     int row = 0, p = 0, end = 0, pidx = -1;
     if (has) {
@@ -241,13 +246,27 @@ __global__ void __launch_bounds__(256) gamma_multi_kernel(const GammaArgs a) {
     if (grp == 0) gamma_row_update<G, V, HYPER>(a, R, gl, group_mask<G>(lane), self, sa, sb);
 }
 
+static int g_tune_interleave = -1;  // -1 = auto (interleave only when peers are attached); 0 / 1 force
 static int g_tune_group = 0;   // 0 = auto; else forced G for nvec <= 16 (8 or 16)
 static int g_tune_unroll = 0;  // 0 = auto; else forced U
 
+static uint32_t gcd_u32(uint32_t x, uint32_t y) {
+    while (y) { const uint32_t t = x % y; x = y; y = t; }
+    return x;
+}
+
 template <int G, int V, int U>
-static int launch_gamma(const GammaArgs& a, bool hyper, cudaStream_t s) {
+static int launch_gamma(const GammaArgs& a_in, bool hyper, cudaStream_t s) {
+    GammaArgs a = a_in;
     if (a.n_seg > 0) {
         const unsigned grid = (unsigned)cdiv((int64_t)a.n_seg * G, 256);
+        const bool interleave = g_tune_interleave < 0 ? a.n_peers > 0 : g_tune_interleave != 0;
+        a.block_stride = 1;
+        if (interleave && grid > 2) {
+            uint32_t st = (uint32_t)(0.6180339887 * grid) | 1u;   // golden-ratio stride: even spread of every length class
+            while (gcd_u32(st, grid) != 1) st += 2;
+            a.block_stride = st % grid;
+        }
         if (hyper) gamma_pass_kernel<G, V, U, true><<<grid, 256, 0, s>>>(a);
         else gamma_pass_kernel<G, V, U, false><<<grid, 256, 0, s>>>(a);
         PMF_LAUNCH_CHECK();
@@ -270,6 +289,7 @@ extern "C" {
 int pmf_tune(const char* key, int value) {
     PMF_REQUIRE(key != nullptr, "key is NULL");
     if (!strcmp(key, "gamma_group")) g_tune_group = value;
+    else if (!strcmp(key, "gamma_interleave")) g_tune_interleave = value;
     else if (!strcmp(key, "gamma_unroll")) g_tune_unroll = value;
     else { set_error("unknown tuning key '%s'", key); return PMF_EINVAL; }
     return PMF_OK;
