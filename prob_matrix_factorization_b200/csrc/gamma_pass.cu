@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256) gamma_multi_kernel(const GammaArgs a) {
     if (grp == 0) gamma_row_update<G, V, HYPER>(a, R, gl, group_mask<G>(lane), self, sa, sb);
 }
 
-static int g_tune_interleave = -1;  // -1 = auto (interleave only when peers are attached); 0 / 1 force
+static int g_tune_interleave = 0;   // 1 = golden-ratio block interleave of the longest-first order (experiment)
 static int g_tune_group = 0;   // 0 = auto; else forced G for nvec <= 16 (8 or 16)
 static int g_tune_unroll = 0;  // 0 = auto; else forced U
 
@@ -260,7 +260,7 @@ static int launch_gamma(const GammaArgs& a_in, bool hyper, cudaStream_t s) {
     GammaArgs a = a_in;
     if (a.n_seg > 0) {
         const unsigned grid = (unsigned)cdiv((int64_t)a.n_seg * G, 256);
-        const bool interleave = g_tune_interleave < 0 ? a.n_peers > 0 : g_tune_interleave != 0;
+        const bool interleave = g_tune_interleave > 0;   // measured slower at N=1 and N=8 (profiles/README.md): off
         a.block_stride = 1;
         if (interleave && grid > 2) {
             uint32_t st = (uint32_t)(0.6180339887 * grid) | 1u;   // golden-ratio stride: even spread of every length class
