@@ -197,28 +197,23 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
     }
 }
 
-// Rows cut into several segments: one WARP per row.  The 32/G groups of the warp each sum every
-// (32/G)-th partial (independent loads in flight), the group sums are folded with shuffles in a fixed
-// order, and group 0 applies the same row update.  Deterministic; no atomics.
+// Rows cut into several segments: one CTA per row.  Its 256/G lane groups each sum every (256/G)-th
+// partial (independent loads in flight, so a row with hundreds of partials costs a few round trips, not
+// hundreds), park their sums in shared memory, and group 0 folds them in group order and applies the
+// same row update.  Deterministic; no atomics.
 template <int G, int V, bool HYPER>
 __global__ void __launch_bounds__(256) gamma_multi_kernel(const GammaArgs a) {
-    constexpr int NG = 32 / G;
+    constexpr int NG = 256 / G;
+    extern __shared__ float s_part[];   // [NG][2*ld]
     const int lane = threadIdx.x & 31;
-    const int gl = lane & (G - 1);
-    const int grp = lane / G;
-    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (wid >= a.n_multi) return;  // warp-uniform
-    const int row = a.multi_row[wid];
-    const int first = a.multi_first[wid], last = a.multi_first[wid + 1];
+    const int gl = threadIdx.x & (G - 1);
+    const int grp = threadIdx.x / G;
+    const int row = a.multi_row[blockIdx.x];
+    const int first = a.multi_first[blockIdx.x], last = a.multi_first[blockIdx.x + 1];
     const int R = a.row_offset + row;
-    float4 self[V], sa[V], sb[V];
+    float4 sa[V], sb[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        const int idx = gl + v * G;
-        self[v] = (idx < a.nvec) ? *reinterpret_cast<const float4*>(a.E_self + (size_t)R * a.ld + idx * 4) : f4_zero();
-        sa[v] = f4_zero();
-        sb[v] = f4_zero();
-    }
+    for (int v = 0; v < V; ++v) { sa[v] = f4_zero(); sb[v] = f4_zero(); }
     for (int q = first + grp; q < last; q += NG) {
         const float* src = a.partial + (size_t)q * 2 * a.ld;
 #pragma unroll
@@ -232,18 +227,40 @@ __global__ void __launch_bounds__(256) gamma_multi_kernel(const GammaArgs a) {
             }
         }
     }
-    __syncwarp();
-#pragma unroll
-    for (int o = G; o < 32; o <<= 1) {   // fold the groups: lanes with equal gl hold the same K-slice
+    const int used = min(NG, last - first);   // groups that saw at least one partial
+    if (grp > 0 && grp < used) {
+        float* dst = s_part + (size_t)grp * 2 * a.ld;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            sa[v].x += __shfl_xor_sync(0xffffffffu, sa[v].x, o);  sb[v].x += __shfl_xor_sync(0xffffffffu, sb[v].x, o);
-            sa[v].y += __shfl_xor_sync(0xffffffffu, sa[v].y, o);  sb[v].y += __shfl_xor_sync(0xffffffffu, sb[v].y, o);
-            sa[v].z += __shfl_xor_sync(0xffffffffu, sa[v].z, o);  sb[v].z += __shfl_xor_sync(0xffffffffu, sb[v].z, o);
-            sa[v].w += __shfl_xor_sync(0xffffffffu, sa[v].w, o);  sb[v].w += __shfl_xor_sync(0xffffffffu, sb[v].w, o);
+            const int idx = gl + v * G;
+            if (idx < a.nvec) {
+                *reinterpret_cast<float4*>(dst + idx * 4) = sa[v];
+                *reinterpret_cast<float4*>(dst + a.ld + idx * 4) = sb[v];
+            }
         }
     }
-    if (grp == 0) gamma_row_update<G, V, HYPER>(a, R, gl, group_mask<G>(lane), self, sa, sb);
+    __syncthreads();
+    if (grp != 0) return;
+    float4 self[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int idx = gl + v * G;
+        self[v] = (idx < a.nvec) ? *reinterpret_cast<const float4*>(a.E_self + (size_t)R * a.ld + idx * 4) : f4_zero();
+    }
+    for (int g = 1; g < used; ++g) {
+        const float* src = s_part + (size_t)g * 2 * a.ld;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int idx = gl + v * G;
+            if (idx < a.nvec) {
+                const float4 pa = *reinterpret_cast<const float4*>(src + idx * 4);
+                const float4 pb = *reinterpret_cast<const float4*>(src + a.ld + idx * 4);
+                sa[v].x += pa.x; sa[v].y += pa.y; sa[v].z += pa.z; sa[v].w += pa.w;
+                sb[v].x += pb.x; sb[v].y += pb.y; sb[v].z += pb.z; sb[v].w += pb.w;
+            }
+        }
+    }
+    gamma_row_update<G, V, HYPER>(a, R, gl, group_mask<G>(lane), self, sa, sb);
 }
 
 static int g_tune_interleave = 0;   // 1 = golden-ratio block interleave of the longest-first order (experiment)
@@ -272,9 +289,10 @@ static int launch_gamma(const GammaArgs& a_in, bool hyper, cudaStream_t s) {
         PMF_LAUNCH_CHECK();
     }
     if (a.n_multi > 0) {
-        const unsigned grid = (unsigned)cdiv((int64_t)a.n_multi * 32, 256);
-        if (hyper) gamma_multi_kernel<G, V, true><<<grid, 256, 0, s>>>(a);
-        else gamma_multi_kernel<G, V, false><<<grid, 256, 0, s>>>(a);
+        const unsigned grid = (unsigned)a.n_multi;
+        const size_t smem = (size_t)(256 / G) * 2 * a.ld * sizeof(float);   // <= 32 KB for every (G, ld) dispatched
+        if (hyper) gamma_multi_kernel<G, V, true><<<grid, 256, smem, s>>>(a);
+        else gamma_multi_kernel<G, V, false><<<grid, 256, smem, s>>>(a);
         PMF_LAUNCH_CHECK();
     }
     return PMF_OK;

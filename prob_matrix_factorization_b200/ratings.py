@@ -149,7 +149,7 @@ class DeviceRatings:
         self.h2d_bytes = self.nnz * 12
         self.rank, self.world = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
         if seg_len is None:
-            seg_len = auto_seg_len(self.nnz // self.world)     # per-GPU share decides the granularity
+            seg_len = auto_seg_len(self.nnz)
         with torch.cuda.device(device):
             by_user = Grouped.build(u_d, i_d, x_d, self.n_users, seg_len)
             by_item = Grouped.build(i_d, u_d, x_d, self.n_items, seg_len)
