@@ -156,8 +156,9 @@ class GammaEngine:
         self._peer = {}
         if self.exchange == "p2p":
             import torch.distributed as dist
-            for name, shape in (("E_theta", (self.N, self.ld)), ("E_beta", (self.M, self.ld))) + \
-                    ((("E_xi", (self.N,)), ("E_eta", (self.M,))) if hyper is not None else ()):
+            # only the factor tables are replicated every pass: E_xi / E_eta are read solely by the rank
+            # that owns the row (rate prior of its own rows), so they are gathered once, at the end
+            for name, shape in (("E_theta", (self.N, self.ld)), ("E_beta", (self.M, self.ld))):
                 self._peer[name] = PeerTable(shape, self.dev)
             self.E_theta, self.E_beta = self._peer["E_theta"].local, self._peer["E_beta"].local
             self._token = torch.zeros(1, dtype=torch.float32, device=self.dev)
@@ -171,10 +172,7 @@ class GammaEngine:
         if hyper is not None:
             v = lambda rows: torch.zeros(rows, dtype=torch.float32, device=self.dev)
             self.rate_xi, self.rate_eta = v(self.N), v(self.M)
-            if self.exchange == "p2p":
-                self.E_xi, self.E_eta = self._peer["E_xi"].local, self._peer["E_eta"].local
-            else:
-                self.E_xi, self.E_eta = v(self.N), v(self.M)
+            self.E_xi, self.E_eta = v(self.N), v(self.M)
         else:
             self.rate_xi = self.E_xi = self.rate_eta = self.E_eta = None
         self.ws_user = ratings.by_user.workspace(self.ld) if ratings.by_user is not None else None
@@ -208,15 +206,14 @@ class GammaEngine:
 
     # -- one pass ------------------------------------------------------------------------------
     def _pass(self, grouped, E_oth, E_self, shp, rte, shape_prior, rate_prior, rate_vec, hyper_rate, hyper_mean,
-              hyper_shape, hyper_rate_prior, ws, peer_E=None, peer_hyper=None):
+              hyper_shape, hyper_rate_prior, ws, peer_E=None):
         if grouped is None:
             return
         _cabi.call("pmf_gamma_pass_p2p", grouped.handle, self.K, self.ld, E_oth.data_ptr(), E_self.data_ptr(),
                    _cabi.ptr(shp), _cabi.ptr(rte), shape_prior, 0.0 if rate_prior is None else rate_prior,
                    _cabi.ptr(rate_vec), _cabi.ptr(hyper_rate), _cabi.ptr(hyper_mean), hyper_shape,
                    hyper_rate_prior, _cabi.ptr(ws), self.n_peers if peer_E is not None else 0,
-                   peer_E.peer_array if peer_E is not None else None,
-                   peer_hyper.peer_array if peer_hyper is not None else None, _cabi.stream_ptr())
+                   peer_E.peer_array if peer_E is not None else None, None, _cabi.stream_ptr())
 
     def _rank_barrier(self):
         """All ranks' pass kernels (and their P2P stores into this replica) are complete after this."""
@@ -228,22 +225,22 @@ class GammaEngine:
         self._pass(self.r.by_user, self.E_beta, self.E_theta, self.shp_theta, self.rte_theta, self.user_shape,
                    self.user_rate, self.E_xi, self.rate_xi, self.E_xi,
                    h["user_shape"] if h else 0.0, h["user_rate_prior"] if h else 0.0, self.ws_user,
-                   self._peer.get("E_theta"), self._peer.get("E_xi"))
+                   self._peer.get("E_theta"))
         if self.exchange == "p2p":
             self._rank_barrier()
         elif self.xu is not None:
-            self.xu.gather(*([self.E_theta] + ([self.E_xi] if h else [])))
+            self.xu.gather(self.E_theta)
 
     def item_pass(self):
         h = self.hyper
         self._pass(self.r.by_item, self.E_theta, self.E_beta, self.shp_beta, self.rte_beta, self.item_shape,
                    self.item_rate, self.E_eta, self.rate_eta, self.E_eta,
                    h["item_shape"] if h else 0.0, h["item_rate_prior"] if h else 0.0, self.ws_item,
-                   self._peer.get("E_beta"), self._peer.get("E_eta"))
+                   self._peer.get("E_beta"))
         if self.exchange == "p2p":
             self._rank_barrier()
         elif self.xi_ is not None:
-            self.xi_.gather(*([self.E_beta] + ([self.E_eta] if h else [])))
+            self.xi_.gather(self.E_beta)
 
     def sweep(self):
         with torch.cuda.device(self.dev):
@@ -267,10 +264,14 @@ class GammaEngine:
 
     def sync_params(self):
         """Multi-GPU: make the Gamma shape/rate tables (only needed as outputs) complete on every rank."""
-        if self.xu is None or not self.keep_params:
+        if self.xu is None:
             return
-        self.xu.gather(*([self.shp_theta, self.rte_theta] + ([self.rate_xi] if self.hyper else [])))
-        self.xi_.gather(*([self.shp_beta, self.rte_beta] + ([self.rate_eta] if self.hyper else [])))
+        if self.hyper:
+            self.xu.gather(self.rate_xi, self.E_xi)
+            self.xi_.gather(self.rate_eta, self.E_eta)
+        if self.keep_params:
+            self.xu.gather(self.shp_theta, self.rte_theta)
+            self.xi_.gather(self.shp_beta, self.rte_beta)
 
     # -- accounting ----------------------------------------------------------------------------
     def algorithmic_bytes_per_sweep(self):

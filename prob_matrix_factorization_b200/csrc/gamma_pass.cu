@@ -103,7 +103,8 @@ __device__ __forceinline__ void gamma_row_update(const GammaArgs& a, int R, int 
             const float hm = a.hyper_shape / hr;          // hpf_cavi.py:94-95
             a.hyper_rate[R] = hr;
             a.hyper_mean[R] = hm;
-            for (int pr = 0; pr < a.n_peers; ++pr) a.peer_hyper_mean[pr][R] = hm;
+            if (a.peer_hyper_mean[0])   // optional: the hyper mean is only read by the row's owner
+                for (int pr = 0; pr < a.n_peers; ++pr) a.peer_hyper_mean[pr][R] = hm;
         }
     }
 }
@@ -279,7 +280,9 @@ static int launch_gamma(const GammaArgs& a_in, bool hyper, cudaStream_t s) {
         const unsigned grid = (unsigned)cdiv((int64_t)a.n_seg * G, 256);
         const bool interleave = g_tune_interleave > 0;   // measured slower at N=1 and N=8 (profiles/README.md): off
         a.block_stride = 1;
-        if (interleave && grid > 2) {
+        if (g_tune_interleave == 2 && grid > 2) {
+            a.block_stride = grid - 1;   // shortest segments first (row completions, hence P2P stores, start early)
+        } else if (interleave && grid > 2) {
             uint32_t st = (uint32_t)(0.6180339887 * grid) | 1u;   // golden-ratio stride: even spread of every length class
             while (gcd_u32(st, grid) != 1) st += 2;
             a.block_stride = st % grid;
@@ -352,7 +355,6 @@ int pmf_gamma_pass_p2p(const pmf_csr* csr, int32_t K, int32_t ld, const float* d
     a.hyper_rate_prior = hyper_rate_prior; a.partial = (float*)d_workspace;
     PMF_REQUIRE(n_peers >= 0 && n_peers <= kMaxPeers, "n_peers=%d outside [0, %d]", n_peers, kMaxPeers);
     PMF_REQUIRE(n_peers == 0 || h_peer_E_self != nullptr, "peer table pointers are NULL");
-    PMF_REQUIRE(n_peers == 0 || d_hyper_rate == nullptr || h_peer_hyper_mean != nullptr, "peer hyper pointers are NULL");
     a.n_peers = n_peers;
     for (int pr = 0; pr < kMaxPeers; ++pr) {
         a.peer_E[pr] = pr < n_peers ? (float*)h_peer_E_self[pr] : nullptr;
