@@ -121,6 +121,28 @@ int pmf_ipc_open(const void* handle64, void** d_ptr);
 int pmf_ipc_close(void* d_ptr);
 int pmf_ipc_free(void* d_ptr);
 
+/* ---- a11: textbook-HPF extras (no reference code exists: docs/Models.tex:583-726 only; PARITY UNPINNED) ----
+ * pmf_gamma_geomean: G = exp(psi(shape)) / rate (the geometric-mean table, exp(E log x)), padding columns 0.
+ * pmf_gamma_pass_digamma: pmf_gamma_pass with the multinomial allocation of docs/Models.tex:652-664,
+ *     phi_k ∝ G_self_k G_oth_k; shape gets sum_t x_t phi_tk, rate keeps the observed-only sum of E_oth
+ *     (hpf_cavi.py:151); writes E_self AND G_self.  K <= 128.
+ * pmf_hpf_elbo: evidence lower bound of observed-only HPF; d_out6 (float64, zeroed by the call) receives
+ *     [0] sum_obs x log sum_k G_th G_be - lgamma(x+1) - sum_k E_th E_be   [1] E log p(theta|xi)  [2] E log p(beta|eta)
+ *     [3] E log p(xi)  [4] E log p(eta)  [5] entropies;   ELBO = their sum.  Row terms cover users
+ *     [user_begin,user_end) and items [item_begin,item_end) (a rank's owned rows), the likelihood the ratings
+ *     of `by_user`. */
+int pmf_gamma_geomean(const float* d_shp, const float* d_rte, int64_t rows, int32_t K, int32_t ld, float* d_G,
+                      void* stream);
+int pmf_gamma_pass_digamma(const pmf_csr* csr, int32_t K, int32_t ld, const float* d_G_oth, const float* d_E_oth,
+                           float* d_G_self, float* d_E_self, float* d_shp, float* d_rte, float shape_prior,
+                           float rate_prior, const float* d_rate_prior_vec, float* d_hyper_rate, float* d_hyper_mean,
+                           float hyper_shape, float hyper_rate_prior, void* d_workspace, void* stream);
+int pmf_hpf_elbo(const pmf_csr* by_user, int32_t K, int32_t ld, const float* d_E_theta, const float* d_E_beta,
+                 const float* d_G_theta, const float* d_G_beta, const float* d_shp_theta, const float* d_rte_theta,
+                 const float* d_shp_beta, const float* d_rte_beta, const float* d_rate_xi, const float* d_rate_eta,
+                 int32_t user_begin, int32_t user_end, int32_t item_begin, int32_t item_end, float a, float a_prime,
+                 float b_prime, float c, float c_prime, float d_prime, double* d_out6, void* stream);
+
 /* ---- a8-a10: predict and evaluation -------------------------------------------------
  * predict (poisson_mf_cavi.py:221-241, hpf_cavi.py:215-231, gaussian_mf_cavi_bias.py:291-316,
  * hpf_pytorch.py:66-69,186-195): pred = <F_user[u], F_item[i]> (+ b_user[u] + b_item[i]) for

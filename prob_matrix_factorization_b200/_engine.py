@@ -273,6 +273,56 @@ class GammaEngine:
             self.xu.gather(self.shp_theta, self.rte_theta)
             self.xi_.gather(self.shp_beta, self.rte_beta)
 
+    # -- a11 extras (single GPU; parity unpinned) ------------------------------------------------
+    def load_params(self, shp_theta, rte_theta, shp_beta, rte_beta, rate_xi, rate_eta):
+        """Upload Gamma shape/rate tables (needed before the first sweep by the digamma pass and the ELBO)."""
+        for name, host in (("shp_theta", shp_theta), ("rte_theta", rte_theta), ("shp_beta", shp_beta), ("rte_beta", rte_beta)):
+            getattr(self, name).copy_(pad_table(host, self.ld, self.dev))
+        self.rate_xi.copy_(to_device(np.asarray(rate_xi, dtype=np.float32), self.dev))
+        self.rate_eta.copy_(to_device(np.asarray(rate_eta, dtype=np.float32), self.dev))
+
+    def geomean_tables(self):
+        """G = exp(psi(shape))/rate for both sides (pmf_gamma_geomean)."""
+        if getattr(self, "G_theta", None) is None:
+            self.G_theta, self.G_beta = torch.zeros_like(self.E_theta), torch.zeros_like(self.E_beta)
+        with torch.cuda.device(self.dev):
+            for shp, rte, G, rows in ((self.shp_theta, self.rte_theta, self.G_theta, self.N),
+                                      (self.shp_beta, self.rte_beta, self.G_beta, self.M)):
+                _cabi.call("pmf_gamma_geomean", shp.data_ptr(), rte.data_ptr(), rows, self.K, self.ld, G.data_ptr(),
+                           _cabi.stream_ptr())
+        return self.G_theta, self.G_beta
+
+    def sweep_digamma(self):
+        """One sweep with the multinomial (digamma) allocation of docs/Models.tex:652-664."""
+        if self.r.world > 1:
+            raise NotImplementedError("digamma allocation is single-GPU in this round")
+        h = self.hyper
+        with torch.cuda.device(self.dev):
+            for grouped, G_oth, E_oth, G_self, E_self, shp, rte, shape, rate_vec, hr, hs, hp, ws in (
+                    (self.r.by_user, self.G_beta, self.E_beta, self.G_theta, self.E_theta, self.shp_theta, self.rte_theta,
+                     self.user_shape, self.E_xi, self.rate_xi, h["user_shape"], h["user_rate_prior"], self.ws_user),
+                    (self.r.by_item, self.G_theta, self.E_theta, self.G_beta, self.E_beta, self.shp_beta, self.rte_beta,
+                     self.item_shape, self.E_eta, self.rate_eta, h["item_shape"], h["item_rate_prior"], self.ws_item)):
+                _cabi.call("pmf_gamma_pass_digamma", grouped.handle, self.K, self.ld, G_oth.data_ptr(), E_oth.data_ptr(),
+                           G_self.data_ptr(), E_self.data_ptr(), shp.data_ptr(), rte.data_ptr(), shape, 0.0,
+                           rate_vec.data_ptr(), hr.data_ptr(), rate_vec.data_ptr(), hs, hp, _cabi.ptr(ws), _cabi.stream_ptr())
+
+    def elbo(self, cfg, refresh_geomean=True):
+        """Observed-only HPF ELBO and its six components (pmf_hpf_elbo); one D2H of 6 doubles."""
+        if self.r.world > 1:
+            raise NotImplementedError("ELBO is single-GPU in this round")
+        if refresh_geomean or getattr(self, "G_theta", None) is None:
+            self.geomean_tables()
+        out = torch.zeros(6, dtype=torch.float64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _cabi.call("pmf_hpf_elbo", self.r.by_user.handle, self.K, self.ld, self.E_theta.data_ptr(), self.E_beta.data_ptr(),
+                       self.G_theta.data_ptr(), self.G_beta.data_ptr(), self.shp_theta.data_ptr(), self.rte_theta.data_ptr(),
+                       self.shp_beta.data_ptr(), self.rte_beta.data_ptr(), self.rate_xi.data_ptr(), self.rate_eta.data_ptr(),
+                       0, self.N, 0, self.M, cfg.a, cfg.a_prime, cfg.b_prime, cfg.c, cfg.c_prime, cfg.d_prime,
+                       out.data_ptr(), _cabi.stream_ptr())
+        parts = out.cpu().numpy()
+        return float(parts.sum()), parts
+
     # -- accounting ----------------------------------------------------------------------------
     def algorithmic_bytes_per_sweep(self):
         """per pass nnz*(4K+8) + R*(16K+4) (+12 R for the HPF hyper vectors)."""

@@ -47,8 +47,17 @@ class HPF_CAVI(_DeviceBacked):
                   "gamma_b_beta": "rte_beta", "gamma_b_xi": "rate_xi", "gamma_b_eta": "rate_eta",
                   "E_theta": "E_theta", "E_beta": "E_beta", "E_xi": "E_xi", "E_eta": "E_eta"}
 
-    def __init__(self, config: HPF_CAVI_Config, device=None, shard=None, seg_len=DEFAULT_SEG_LEN):
+    def __init__(self, config: HPF_CAVI_Config, device=None, shard=None, seg_len=DEFAULT_SEG_LEN,
+                 allocation="mean", track_elbo=False):
+        """``allocation="mean"`` is the reference code's update (arithmetic means, hpf_cavi.py:140-151);
+        ``"digamma"`` is the textbook multinomial step of docs/Models.tex:652-664 (no reference code; parity
+        unpinned).  ``track_elbo`` records the ELBO after every sweep in ``elbo_history_``."""
+        if allocation not in ("mean", "digamma"):
+            raise ValueError("allocation must be 'mean' or 'digamma'")
         self._init_backing()
+        self._allocation = allocation
+        self._track_elbo = bool(track_elbo)
+        self.elbo_history_ = []
         self.config = config
         self.n_users = None
         self.n_items = None
@@ -124,6 +133,11 @@ class HPF_CAVI(_DeviceBacked):
                  "item_shape": float(init["gamma_a_eta"]), "item_rate_prior": float(cfg.d_prime)}
         eng = GammaEngine(dr, cfg.n_factors, cfg.a, cfg.c, None, None, hyper=hyper)
         eng.load_means(init["E_theta"], init["E_beta"], init["E_xi"], init["E_eta"])
+        if self._allocation == "digamma" or self._track_elbo:
+            eng.load_params(init["gamma_a_theta"], init["gamma_b_theta"], init["gamma_a_beta"], init["gamma_b_beta"],
+                            init["gamma_b_xi"], init["gamma_b_eta"])
+            eng.geomean_tables()
+        self.elbo_history_ = []
         self._engine = eng
         self._init = init
         self._invalidate()
@@ -136,8 +150,13 @@ class HPF_CAVI(_DeviceBacked):
         for it in range(1, cfg.max_iter + 1):
             if cfg.verbose:
                 print(f"\nHPF_CAVI iteration {it}/{cfg.max_iter}")
-            eng.sweep()
+            if self._allocation == "digamma":
+                eng.sweep_digamma()
+            else:
+                eng.sweep()
             self.n_iter_ = it
+            if self._track_elbo:
+                self.elbo_history_.append(eng.elbo(cfg, refresh_geomean=self._allocation != "digamma")[0])
             if ev is not None:
                 st = self._eval(ev)
                 val_rmse, val_macro_mae = st["rmse"], st["macro_mae"]
@@ -160,6 +179,18 @@ class HPF_CAVI(_DeviceBacked):
             self._init = None
         self._invalidate()
         return self
+
+    def elbo(self, return_parts=False):
+        """Evidence lower bound of the current variational state (observed-only HPF; parity unpinned)."""
+        e = self._engine
+        if e is None:
+            raise RuntimeError("fit() must be called before elbo()")
+        if self.n_iter_ == 0 and self._init is not None and not (self._allocation == "digamma" or self._track_elbo):
+            i = self._init
+            e.load_params(i["gamma_a_theta"], i["gamma_b_theta"], i["gamma_a_beta"], i["gamma_b_beta"],
+                          i["gamma_b_xi"], i["gamma_b_eta"])
+        total, parts = e.elbo(self.config, refresh_geomean=True)
+        return (total, parts) if return_parts else total
 
     def _eval(self, ev):
         e = self._engine
