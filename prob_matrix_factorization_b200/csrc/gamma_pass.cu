@@ -138,11 +138,16 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
     }
     // warp-uniform trip count so that full-mask shuffles are legal; short groups idle on predicates
     const int maxlen = __reduce_max_sync(0xffffffffu, end - p);
+    // column ids / ratings are fetched one chunk ahead, so the dependent chain per chunk is one memory
+    // latency (the gathered rows), not two (ids, then rows)
+    int c_nxt = (p + gl < end) ? __ldg(a.col + p + gl) : 0;
+    float x_nxt = (p + gl < end) ? __ldg(a.val + p + gl) : 0.f;
     for (int base = 0; base < maxlen; base += G) {
-        const int q = p + base + gl;
-        const bool okq = q < end;
-        const int c_l = okq ? __ldg(a.col + q) : 0;
-        const float x_l = okq ? __ldg(a.val + q) : 0.f;
+        const int c_l = c_nxt;
+        const float x_l = x_nxt;
+        const int qn = p + base + G + gl;
+        c_nxt = qn < end ? __ldg(a.col + qn) : 0;
+        x_nxt = qn < end ? __ldg(a.val + qn) : 0.f;
         const int rem = end - (p + base);
 #pragma unroll
         for (int j0 = 0; j0 < G; j0 += U) {
