@@ -143,6 +143,19 @@ int pmf_hpf_elbo(const pmf_csr* by_user, int32_t K, int32_t ld, const float* d_E
                  int32_t user_begin, int32_t user_end, int32_t item_begin, int32_t item_end, float a, float a_prime,
                  float b_prime, float c, float c_prime, float d_prime, double* d_out6, void* stream);
 
+/* Dense U V^T top-n scoring (evaluation; the one GEMM-shaped step, so the one use of tensor cores).
+ * For each of `batch_rows` user rows (row b = d_user_rows ? d_user_rows[b] : b of d_F_user) the n best items by
+ *   score = float32 chain  s = s + u[k]*v[k], k = 0..K-1 (separate multiply and add),
+ * ranked by (score descending, item index ascending); d_idx / d_score are [batch_rows][n].
+ * tensor_cores != 0: approximate scores by tcgen05.mma (bf16 operands, fp32 accumulation in TMEM), then an exact
+ * fp32 re-score of a provably sufficient candidate set, so indices are identical to tensor_cores == 0 (exact
+ * CUDA-core scoring).  d_stats (int32[2], may be NULL): rows that fell back to exact scoring, candidates re-scored.
+ * PARITY UNPINNED: the reference has no top-n code; semantics = oracle/pmf_oracle.py::topn. */
+int64_t pmf_topn_workspace_bytes(int64_t batch_rows, int32_t n_items, int32_t K);
+int pmf_topn(const float* d_F_user, const int32_t* d_user_rows, int64_t batch_rows, const float* d_F_item,
+             int32_t n_items, int32_t K, int32_t ld, int32_t n, int32_t tensor_cores, int32_t* d_idx, float* d_score,
+             void* d_workspace, int64_t workspace_bytes, int32_t* d_stats, void* stream);
+
 /* ---- a8-a10: predict and evaluation -------------------------------------------------
  * predict (poisson_mf_cavi.py:221-241, hpf_cavi.py:215-231, gaussian_mf_cavi_bias.py:291-316,
  * hpf_pytorch.py:66-69,186-195): pred = <F_user[u], F_item[i]> (+ b_user[u] + b_item[i]) for

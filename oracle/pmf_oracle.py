@@ -499,7 +499,8 @@ def topn(F_user, F_item, n, user_rows=None):
         Fu = Fu[user_rows]
     scores = np.zeros((Fu.shape[0], Fi.shape[0]), np.float32)
     for k in range(Fu.shape[1]):
-        scores = np.float32(scores + Fu[:, k:k + 1] * Fi[None, :, k])
-    order = np.lexsort((np.broadcast_to(np.arange(Fi.shape[0]), scores.shape), -scores), axis=1)
-    idx = order[:, :n]
+        prod = (Fu[:, k:k + 1] * Fi[None, :, k]).astype(np.float32)      # rounded product ...
+        scores = (scores + prod).astype(np.float32)                       # ... then rounded add (no FMA)
+    items = np.arange(Fi.shape[0])
+    idx = np.stack([np.lexsort((items, -row))[:n] for row in scores])     # score desc, then index asc
     return idx.astype(np.int32), np.take_along_axis(scores, idx, axis=1)
