@@ -1,0 +1,73 @@
+"""Full BASELINE.json sizes on the GPU, checked through size-independent properties (the oracle cannot run
+these sizes in seconds):
+
+* grouping: perm is a permutation, keys sorted, original order kept inside every row (= stable), row_ptr consistent;
+* a Gamma-Poisson pass conserves mass:   sum_k shape[r,k] - K*prior = sum_{t in row r} x_t   (the allocation of a
+  rating sums to the rating over k whenever its rate is above the 1e-10 floor), and is linear in the gathered rows:
+  sum_r (rate[r,:] - prior_r) = sum_j count_j * E_oth[j,:];
+* the HPF hyper update satisfies b_xi = b' + sum_k E_theta exactly as stored.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HP = dict(a=0.3, a_prime=5.0, b_prime=5.0, c=0.3, c_prime=5.0, d_prime=5.0)
+
+
+def check_grouping(g, key, n_rows):
+    perm = g.perm().astype(np.int64)
+    row_ptr = g.row_ptr().astype(np.int64)
+    nnz = len(key)
+    assert row_ptr[0] == 0 and row_ptr[-1] == nnz and np.all(np.diff(row_ptr) >= 0)
+    seen = np.zeros(nnz, dtype=bool); seen[perm] = True
+    assert seen.all()                                            # a permutation
+    sk = key[perm]
+    assert np.all(np.diff(sk) >= 0)                              # sorted by key
+    same = sk[1:] == sk[:-1]
+    assert np.all(perm[1:][same] > perm[:-1][same])              # stable: original order inside a row
+    assert np.array_equal(np.diff(row_ptr), np.bincount(key, minlength=n_rows))
+
+
+@pytest.mark.parametrize("name", ["c2", "c5"])
+def test_full_size_properties(name):
+    from prob_matrix_factorization_b200 import synth
+    from prob_matrix_factorization_b200.hpf_cavi import HPF_CAVI, HPF_CAVI_Config
+    w, (u, i, x) = synth.workload_ratings(name)
+    x = x + np.float32(1.0)
+    K = w.n_factors
+    m = HPF_CAVI(HPF_CAVI_Config(n_factors=K, max_iter=1, tol=None, verbose=False, **HP))
+    m.n_users, m.n_items = w.n_users, w.n_items
+    rng = np.random.default_rng(1)                               # cheap positive initial state (properties do not need PCG parity)
+    init = {"gamma_a_xi": HP["a_prime"] + K * HP["a"], "gamma_a_eta": HP["c_prime"] + K * HP["c"],
+            "E_theta": rng.random((w.n_users, K), dtype=np.float32) + 0.05,
+            "E_beta": rng.random((w.n_items, K), dtype=np.float32) + 0.05,
+            "E_xi": np.full(w.n_users, 1.3, np.float32), "E_eta": np.full(w.n_items, 0.9, np.float32)}
+    m.fit_arrays(u, i, x, init)
+    e = m._engine
+    check_grouping(e.r.by_user, u.astype(np.int64), w.n_users)
+    if name == "c2":
+        check_grouping(e.r.by_item, i.astype(np.int64), w.n_items)
+    dev = e.dev
+    ud = torch.from_numpy(u.astype(np.int64)).to(dev); idd = torch.from_numpy(i.astype(np.int64)).to(dev)
+    xd = torch.from_numpy(x).to(dev).double()
+    # mass conservation of the user pass (shape) -- float32 sums over up to 1e4 ratings: 1e-5 relative
+    mass_u = torch.zeros(w.n_users, dtype=torch.float64, device=dev).index_add_(0, ud, xd)
+    got = e.shp_theta[:, :K].double().sum(1) - K * HP["a"]
+    assert torch.max(torch.abs(got - mass_u) / (mass_u + 1.0)).item() < 1e-5
+    mass_i = torch.zeros(w.n_items, dtype=torch.float64, device=dev).index_add_(0, idd, xd)
+    got = e.shp_beta[:, :K].double().sum(1) - K * HP["c"]
+    assert torch.max(torch.abs(got - mass_i) / (mass_i + 1.0)).item() < 1e-5
+    # linearity of the rate sums: user side gathered the INITIAL E_beta, item side the NEW E_theta
+    cnt_i = torch.bincount(idd, minlength=w.n_items).double()
+    lhs = (e.rte_theta[:, :K].double() - torch.from_numpy(init["E_xi"]).to(dev).double()[:, None]).sum(0)
+    rhs = (cnt_i[:, None] * torch.from_numpy(init["E_beta"]).to(dev).double()).sum(0)
+    assert torch.max(torch.abs(lhs - rhs) / rhs).item() < 1e-5
+    cnt_u = torch.bincount(ud, minlength=w.n_users).double()
+    lhs = (e.rte_beta[:, :K].double() - torch.from_numpy(init["E_eta"]).to(dev).double()[:, None]).sum(0)
+    rhs = (cnt_u[:, None] * e.E_theta[:, :K].double()).sum(0)
+    assert torch.max(torch.abs(lhs - rhs) / rhs).item() < 1e-5
+    # hyper update and mean = shape / rate, as stored
+    assert torch.allclose(e.rate_xi, HP["b_prime"] + e.E_theta[:, :K].sum(1), rtol=2e-6)
+    assert torch.allclose(e.E_theta[:, :K], e.shp_theta[:, :K] / e.rte_theta[:, :K], rtol=1e-6)
+    assert torch.all(e.E_theta[:, K:] == 0) and torch.all(e.E_beta[:, K:] == 0)      # padding never leaks

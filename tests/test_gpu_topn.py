@@ -26,7 +26,7 @@ def test_topn_matches_oracle(tensor, B, M, K, n, kind):
     assert np.array_equal(idx, ref_idx)
     assert np.array_equal(score, ref_score)          # same float32 chain -> identical bits
     if tensor:
-        assert stats["candidates_rescored"] >= B * n
+        assert stats["candidates_rescored"] >= B * n and stats["exact_fallback_rows"] == 0
 
 
 @pytest.mark.parametrize("tensor", [False, True])
