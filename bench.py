@@ -241,7 +241,7 @@ def main():
     ap.add_argument("--seg-len", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--exchange", default=None, choices=["p2p", "nccl"], help="multi-GPU row exchange (default p2p)")
+    ap.add_argument("--exchange", default=None, choices=["p2p", "nccl", "mc"], help="multi-GPU row exchange (default p2p)")
     ap.add_argument("--tune", default="", help="comma list key=value passed to pmf_tune (experiments)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -388,6 +388,8 @@ def main():
                        "sharding": "ratings by nonzero (row-aligned), factors replicated" if world > 1 else "single GPU",
                        "row_exchange": {"p2p": "fused into the pass kernel: P2P stores to peer replicas over NVLink + "
                                                "1-element NCCL all-reduce as inter-pass barrier",
+                                        "mc": "fused into the pass kernel: one multimem.st per row slice, replicated to all "
+                                              "GPUs by the NVSwitch (multicast) + signal-pad barrier between passes",
                                         "nccl": "NCCL all-gather of owned rows after each pass",
                                         "none": None}[eng.exchange],
                        "l2": (f"working set {ws_gb:.2f} GB (ratings + factor tables) vs 126 MB L2: "

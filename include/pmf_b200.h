@@ -108,7 +108,9 @@ int pmf_gamma_pass(const pmf_csr* csr, int32_t K, int32_t ld,
  * through peer-mapped pointers (NVLink P2P stores), so the transfer overlaps the pass tile by tile and no
  * separate all-gather is needed; callers barrier across ranks between passes.  h_peer_* are HOST arrays of
  * n_peers (<= 7) device pointers obtained from pmf_ipc_open; h_peer_hyper_mean may be NULL (the hyper mean
- * is only read by the rank that owns the row, so replicas can be refreshed once after the last sweep). */
+ * is only read by the rank that owns the row, so replicas can be refreshed once after the last sweep).
+ * n_peers == -1: h_peer_E_self[0] is an NVSwitch MULTICAST address of E_self; each finished row is then pushed
+ * to every replica with one multimem.st (in-switch replication) instead of one store per peer. */
 int pmf_gamma_pass_p2p(const pmf_csr* csr, int32_t K, int32_t ld,
                        const float* d_E_oth, float* d_E_self, float* d_shp, float* d_rte,
                        float shape_prior, float rate_prior, const float* d_rate_prior_vec,

@@ -154,7 +154,18 @@ class GammaEngine:
             exchange = os.environ.get("PMF_EXCHANGE", "p2p")
         self.exchange = exchange if ratings.world > 1 else "none"
         self._peer = {}
-        if self.exchange == "p2p":
+        self._symm = {}
+        if self.exchange == "mc":
+            try:
+                self._setup_multicast()
+            except Exception as exc:  # multicast needs NVSwitch + driver support: fall back to plain P2P stores
+                import warnings
+                warnings.warn(f"multicast row exchange unavailable ({exc}); using P2P stores")
+                self._symm = {}
+                self.exchange = "p2p"
+        if self.exchange == "mc":
+            self.E_theta, self.E_beta = self._symm["E_theta"][0], self._symm["E_beta"][0]
+        elif self.exchange == "p2p":
             import torch.distributed as dist
             # only the factor tables are replicated every pass: E_xi / E_eta are read solely by the rank
             # that owns the row (rate prior of its own rows), so they are gathered once, at the end
@@ -179,7 +190,7 @@ class GammaEngine:
         self.ws_item = ratings.by_item.workspace(self.ld) if ratings.by_item is not None else None
         self.xu = RowExchange(ratings.user_bounds) if ratings.world > 1 else None
         self.xi_ = RowExchange(ratings.item_bounds) if ratings.world > 1 else None
-        self.n_peers = ratings.world - 1 if self.exchange == "p2p" else 0
+        self.n_peers = ratings.world - 1 if self.exchange == "p2p" else (-1 if self.exchange == "mc" else 0)
         self.launches_per_sweep = sum(
             (1 if g.n_segments > 0 else 0) + (1 if g.n_multi_rows > 0 else 0)
             for g in (ratings.by_user, ratings.by_item) if g is not None)
@@ -213,10 +224,28 @@ class GammaEngine:
                    _cabi.ptr(shp), _cabi.ptr(rte), shape_prior, 0.0 if rate_prior is None else rate_prior,
                    _cabi.ptr(rate_vec), _cabi.ptr(hyper_rate), _cabi.ptr(hyper_mean), hyper_shape,
                    hyper_rate_prior, _cabi.ptr(ws), self.n_peers if peer_E is not None else 0,
-                   peer_E.peer_array if peer_E is not None else None, None, _cabi.stream_ptr())
+                   peer_E if peer_E is not None else None, None, _cabi.stream_ptr())
+
+    def _setup_multicast(self):
+        """E_theta / E_beta in torch symmetric memory with an NVSwitch multicast alias (plumbing only)."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = dist.group.WORLD
+        for name, rows in (("E_theta", self.N), ("E_beta", self.M)):
+            t = symm_mem.empty((rows, self.ld), dtype=torch.float32, device=self.dev)
+            hdl = symm_mem.rendezvous(t, group.group_name)
+            if not hdl.multicast_ptr:
+                raise RuntimeError("no multicast pointer")
+            t.zero_()
+            self._symm[name] = (t, hdl, (C.c_void_p * 1)(hdl.multicast_ptr))
+        torch.cuda.synchronize(self.dev)
+        dist.barrier()
 
     def _rank_barrier(self):
-        """All ranks' pass kernels (and their P2P stores into this replica) are complete after this."""
+        """All ranks' pass kernels (and their remote stores into this replica) are complete after this."""
+        if self.exchange == "mc":
+            self._symm["E_theta"][1].barrier(channel=0)      # device-side signal-pad barrier on the current stream
+            return
         import torch.distributed as dist
         dist.all_reduce(self._token)
 
@@ -225,8 +254,8 @@ class GammaEngine:
         self._pass(self.r.by_user, self.E_beta, self.E_theta, self.shp_theta, self.rte_theta, self.user_shape,
                    self.user_rate, self.E_xi, self.rate_xi, self.E_xi,
                    h["user_shape"] if h else 0.0, h["user_rate_prior"] if h else 0.0, self.ws_user,
-                   self._peer.get("E_theta"))
-        if self.exchange == "p2p":
+                   self._remote("E_theta"))
+        if self.exchange in ("p2p", "mc"):
             self._rank_barrier()
         elif self.xu is not None:
             self.xu.gather(self.E_theta)
@@ -236,8 +265,8 @@ class GammaEngine:
         self._pass(self.r.by_item, self.E_theta, self.E_beta, self.shp_beta, self.rte_beta, self.item_shape,
                    self.item_rate, self.E_eta, self.rate_eta, self.E_eta,
                    h["item_shape"] if h else 0.0, h["item_rate_prior"] if h else 0.0, self.ws_item,
-                   self._peer.get("E_beta"))
-        if self.exchange == "p2p":
+                   self._remote("E_beta"))
+        if self.exchange in ("p2p", "mc"):
             self._rank_barrier()
         elif self.xi_ is not None:
             self.xi_.gather(self.E_beta)
@@ -247,8 +276,25 @@ class GammaEngine:
             self.user_pass()
             self.item_pass()
 
+    def _remote(self, name):
+        """ctypes array of remote aliases of a table for pmf_gamma_pass_p2p (peers, or the multicast address)."""
+        if self.exchange == "p2p":
+            return self._peer[name].peer_array
+        if self.exchange == "mc":
+            return self._symm[name][2]
+        return None
+
     def close(self):
         """Unmap / free peer-shared tables (multi-GPU p2p exchange).  Call on every rank."""
+        if self._symm:
+            import torch.distributed as dist
+            torch.cuda.synchronize(self.dev)
+            dist.barrier()
+            for k, (t, hdl, arr) in self._symm.items():
+                setattr(self, k, t.clone())
+            self._symm = {}
+            self.exchange = "closed"
+            self.n_peers = 0
         if self._peer:
             import torch.distributed as dist
             keep = {k: getattr(self, k).clone() for k in self._peer}     # state stays readable after close

@@ -45,6 +45,7 @@ struct GammaArgs {
     // segments over the launch so that row completions (= P2P row stores) are spread over the whole kernel.
     uint32_t block_stride;
     int32_t n_peers;
+    float* mc_E;   // NVSwitch multicast alias of E_self (all replicas at once, multimem.st) or NULL
     float* peer_E[kMaxPeers];
     float* peer_hyper_mean[kMaxPeers];
 };
@@ -93,6 +94,9 @@ __device__ __forceinline__ void gamma_row_update(const GammaArgs& a, int R, int 
             *reinterpret_cast<float4*>(a.E_self + rowoff + k0) = e;
             for (int pr = 0; pr < a.n_peers; ++pr)   // P2P stores: 16*G contiguous bytes per group and peer
                 *reinterpret_cast<float4*>(a.peer_E[pr] + rowoff + k0) = e;
+            if (a.mc_E)   // one store, replicated to every GPU of the multicast group by the NVSwitch
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                             ::"l"(a.mc_E + rowoff + k0), "f"(e.x), "f"(e.y), "f"(e.z), "f"(e.w) : "memory");
             esum += (e.x + e.y) + (e.z + e.w);
         }
     }
@@ -358,8 +362,13 @@ int pmf_gamma_pass_p2p(const pmf_csr* csr, int32_t K, int32_t ld, const float* d
     a.shape_prior = shape_prior; a.rate_prior = rate_prior; a.rate_prior_vec = d_rate_prior_vec;
     a.hyper_rate = d_hyper_rate; a.hyper_mean = d_hyper_mean; a.hyper_shape = hyper_shape;
     a.hyper_rate_prior = hyper_rate_prior; a.partial = (float*)d_workspace;
-    PMF_REQUIRE(n_peers >= 0 && n_peers <= kMaxPeers, "n_peers=%d outside [0, %d]", n_peers, kMaxPeers);
+    PMF_REQUIRE(n_peers >= -1 && n_peers <= kMaxPeers, "n_peers=%d outside [-1, %d]", n_peers, kMaxPeers);
     PMF_REQUIRE(n_peers == 0 || h_peer_E_self != nullptr, "peer table pointers are NULL");
+    a.mc_E = nullptr;
+    if (n_peers == -1) {   // multicast mode: h_peer_E_self[0] is the multicast address of E_self
+        a.mc_E = (float*)h_peer_E_self[0];
+        n_peers = 0;
+    }
     a.n_peers = n_peers;
     for (int pr = 0; pr < kMaxPeers; ++pr) {
         a.peer_E[pr] = pr < n_peers ? (float*)h_peer_E_self[pr] : nullptr;

@@ -39,7 +39,7 @@ def main():
     for k in ("gamma_a_theta", "gamma_b_theta", "gamma_a_beta", "gamma_b_beta", "gamma_b_xi", "gamma_b_eta",
               "E_theta", "E_beta", "E_xi", "E_eta"):
         worst = max(worst, rel_max(getattr(m, k), ref[k]))
-    assert m._engine.exchange == "closed" if os.environ["PMF_EXCHANGE"] == "p2p" else m._engine.exchange == "nccl"
+    assert m._engine.exchange == ("nccl" if os.environ["PMF_EXCHANGE"] == "nccl" else "closed")
     # every rank must hold the same replicated tables bit for bit
     h = torch.stack([m._engine.E_theta.double().sum(), m._engine.E_beta.double().sum()])
     hs = [torch.zeros_like(h) for _ in range(world)]
