@@ -148,19 +148,27 @@ class GammaEngine:
         self.hyper = hyper
         self.keep_params = keep_params
         f = lambda rows: torch.zeros((rows, self.ld), dtype=torch.float32, device=self.dev)
-        # multi-GPU row exchange: "p2p" = fused into the pass kernel over peer-mapped replicas (default),
-        # "nccl" = all-gather of owned rows after the pass
+        # multi-GPU row exchange, all fused into the pass kernel except "nccl":
+        #   "mc"   one multimem.st per row slice, replicated by the NVSwitch (default; falls back to "p2p")
+        #   "p2p"  one store per peer into CUDA-IPC mapped replicas
+        #   "nccl" all-gather of owned rows after the pass
         if exchange is None:
-            exchange = os.environ.get("PMF_EXCHANGE", "p2p")
+            exchange = os.environ.get("PMF_EXCHANGE", "mc")
         self.exchange = exchange if ratings.world > 1 else "none"
         self._peer = {}
         self._symm = {}
         if self.exchange == "mc":
+            import torch.distributed as dist
+            ok, why = 1.0, ""
             try:
                 self._setup_multicast()
-            except Exception as exc:  # multicast needs NVSwitch + driver support: fall back to plain P2P stores
+            except Exception as exc:  # multicast needs NVSwitch + driver support
+                ok, why = 0.0, str(exc)
+            flag = torch.tensor([ok], device=self.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # the fallback decision is collective
+            if flag.item() < 1.0:
                 import warnings
-                warnings.warn(f"multicast row exchange unavailable ({exc}); using P2P stores")
+                warnings.warn(f"multicast row exchange unavailable ({why or 'on another rank'}); using P2P stores")
                 self._symm = {}
                 self.exchange = "p2p"
         if self.exchange == "mc":
@@ -239,7 +247,6 @@ class GammaEngine:
             t.zero_()
             self._symm[name] = (t, hdl, (C.c_void_p * 1)(hdl.multicast_ptr))
         torch.cuda.synchronize(self.dev)
-        dist.barrier()
 
     def _rank_barrier(self):
         """All ranks' pass kernels (and their remote stores into this replica) are complete after this."""

@@ -52,7 +52,7 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(f"EXP {combo:40s} seg_len={eng.r.by_user.seg_len:5d} user {tt[0]:.3f} item {tt[1]:.3f} step {tt[2]:.3f} ms "
+            print(f"EXP [{eng.exchange}] {combo:40s} seg_len={eng.r.by_user.seg_len:5d} user {tt[0]:.3f} item {tt[1]:.3f} step {tt[2]:.3f} ms "
                   f"-> {w.nnz / (tt[2].item() * 1e-3):.3e} nnz*it/s", flush=True)
         eng.close()
         m._engine = None
