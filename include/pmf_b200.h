@@ -225,6 +225,29 @@ int pmf_hpf_map_loss_grad(const void* d_users, const void* d_items, int32_t id_b
 int pmf_adam_dense_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
                         float beta1, float beta2, float eps, float step_size, float bias_correction2_sqrt,
                         void* stream);
+/* Lazy ("touch-only") Adam, exactly equivalent to the dense update: rows without gradient are replayed in
+ * registers when next touched.  All arrays are device memory owned by the caller:
+ * parameters, first/second moments and dense gradient scratch for theta (N,K), beta (M,K), xi (N), eta (M);
+ * last_* / claim_* int32 per row (zero-initialised: "up to date with step 0"); touched_* int32[batch];
+ * counters int32[2]; step_size[s] = lr/(1-beta1^s) and bc2_sqrt[s] = sqrt(1-beta2^s) for every step s (1-based). */
+typedef struct pmf_lazy_adam {
+    float *theta, *beta, *xi, *eta;
+    float *m_theta, *m_beta, *m_xi, *m_eta;
+    float *v_theta, *v_beta, *v_xi, *v_eta;
+    float *g_theta, *g_beta, *g_xi, *g_eta;
+    int32_t *last_user, *last_item, *claim_user, *claim_item, *touched_user, *touched_item, *counters;
+    const float *step_size, *bc2_sqrt;
+    float beta1, beta2, eps;
+} pmf_lazy_adam;
+/* One pass over n (already shuffled) ratings in mini-batches of `batch`: per step catch the batch's rows up,
+ * fused loss+gradient, Adam step on the touched rows.  step0 = steps taken so far; adds the losses to *d_loss. */
+int pmf_hpf_map_lazy_epoch(const pmf_lazy_adam* st, const void* d_users, const void* d_items, int32_t id_bytes,
+                           const float* d_ratings, int64_t n, int64_t batch, int64_t step0, const float* d_user_scale,
+                           const float* d_item_scale, int32_t N, int32_t M, int32_t K, float a, float a_prime,
+                           float b_prime, float c, float c_prime, float d_prime, double* d_loss, int32_t* d_bad,
+                           void* stream);
+/* Bring every row up to step_now (before parameters are read from outside the lazy loop). */
+int pmf_hpf_map_lazy_flush(const pmf_lazy_adam* st, int32_t N, int32_t M, int32_t K, int64_t step_now, void* stream);
 int pmf_hpf_map_predict(const void* d_users, const void* d_items, int32_t id_bytes, int64_t n,
                         const float* d_theta_raw, const float* d_beta_raw, int32_t N, int32_t M, int32_t K,
                         float* d_out, void* stream);

@@ -24,6 +24,16 @@ c_f64p = C.POINTER(C.c_double)
 VP = C.c_void_p
 
 
+class LazyAdamState(C.Structure):
+    """Mirror of ``pmf_lazy_adam`` (include/pmf_b200.h)."""
+
+    _fields_ = ([(n, VP) for n in ("theta", "beta", "xi", "eta", "m_theta", "m_beta", "m_xi", "m_eta", "v_theta", "v_beta",
+                                   "v_xi", "v_eta", "g_theta", "g_beta", "g_xi", "g_eta", "last_user", "last_item",
+                                   "claim_user", "claim_item", "touched_user", "touched_item", "counters", "step_size",
+                                   "bc2_sqrt")]
+                + [("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)])
+
+
 class PMFError(RuntimeError):
     """A libpmf_b200 entry point returned a non-zero status."""
 
@@ -74,6 +84,9 @@ _PROTOTYPES = {
     "pmf_hpf_map_loss_grad": (C.c_int, [VP, VP, C.c_int32, VP, C.c_int64, VP, VP, VP, VP, VP, VP, C.c_int32, C.c_int32,
                                         C.c_int32] + [C.c_float] * 6 + [VP, VP, VP, VP, VP, VP, VP]),
     "pmf_adam_dense_step": (C.c_int, [VP, VP, VP, VP, C.c_int64] + [C.c_float] * 5 + [VP]),
+    "pmf_hpf_map_lazy_epoch": (C.c_int, [C.POINTER(LazyAdamState), VP, VP, C.c_int32, VP, C.c_int64, C.c_int64, C.c_int64, VP, VP,
+                                         C.c_int32, C.c_int32, C.c_int32] + [C.c_float] * 6 + [VP, VP, VP]),
+    "pmf_hpf_map_lazy_flush": (C.c_int, [C.POINTER(LazyAdamState), C.c_int32, C.c_int32, C.c_int32, C.c_int64, VP]),
     "pmf_hpf_map_predict": (C.c_int, [VP, VP, C.c_int32, C.c_int64, VP, VP, C.c_int32, C.c_int32, C.c_int32, VP, VP]),
     "pmf_predict": (C.c_int, [VP, VP, C.c_int64, VP, C.c_int32, VP, C.c_int32, C.c_int32, C.c_int32,
                               VP, VP, C.c_float, C.c_int32, VP, VP]),

@@ -147,6 +147,132 @@ __global__ void __launch_bounds__(256) hpf_map_predict_kernel(const void* users,
     if (lane == 0) out[wid] = acc;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Lazy ("touch-only") Adam, exactly equivalent to torch's dense Adam.
+// torch.optim.Adam updates EVERY row at EVERY step: a row without gradient still decays m and v and moves
+// by -step_size*m/(sqrt(v)/bc2+eps).  Those zero-gradient steps depend only on the row's own (p, m, v) and on
+// per-step scalars, so they can be replayed in registers when the row is next touched: each row remembers the
+// last step it is up to date with (`last`); before a step's gradients are computed every row of the batch is
+// caught up to step t-1, after them only the touched rows take step t.  Traffic per step drops from
+// (N+M)(K+1)*28 bytes to the touched rows; arithmetic and results stay those of the dense kernel above.
+// ------------------------------------------------------------------------------------------------
+struct LazyState {   // mirrors pmf_lazy_adam in pmf_b200.h
+    float *p[4], *m[4], *v[4], *g[4];          // theta (N,K), beta (M,K), xi (N), eta (M)
+    int32_t *last_user, *last_item, *claim_user, *claim_item, *touched_user, *touched_item, *counters;
+    const float *step_size, *bc2_sqrt;          // indexed by step number (1-based)
+    float beta1, beta2, eps;
+};
+
+__device__ __forceinline__ void adam_zero_grad_steps(float& p, float& m, float& v, int from, int to, const LazyState& L) {
+    for (int s = from; s <= to; ++s) {          // same expressions as adam_dense_kernel with grad = 0
+        m = m + (0.f - m) * (1.f - L.beta1);
+        v = v * L.beta2 + (1.f - L.beta2) * 0.f * 0.f;
+        const float denom = sqrtf(v) / L.bc2_sqrt[s] + L.eps;
+        p = p - L.step_size[s] * (m / denom);
+    }
+}
+
+__device__ __forceinline__ void adam_one_step(float& p, float& m, float& v, float g, int s, const LazyState& L) {
+    m = m + (g - m) * (1.f - L.beta1);
+    v = v * L.beta2 + (1.f - L.beta2) * g * g;
+    const float denom = sqrtf(v) / L.bc2_sqrt[s] + L.eps;
+    p = p - L.step_size[s] * (m / denom);
+}
+
+// catch one row (factor row `mat`: 0 theta / 1 beta, plus its scalar 2 xi / 3 eta) up to step t-1, zero its gradient
+template <int G>
+__device__ __forceinline__ void lazy_catch_up_row(const LazyState& L, int mat, int64_t row, int K, int t, int gl, int32_t* last) {
+    const int from = last[row] + 1, to = t - 1;
+    float* P = L.p[mat] + (size_t)row * K; float* Mo = L.m[mat] + (size_t)row * K; float* Vo = L.v[mat] + (size_t)row * K;
+    for (int k = gl; k < K; k += G) {
+        float p = P[k], m = Mo[k], v = Vo[k];
+        adam_zero_grad_steps(p, m, v, from, to, L);
+        P[k] = p; Mo[k] = m; Vo[k] = v;
+        L.g[mat][(size_t)row * K + k] = 0.f;
+    }
+    if (gl == 0) {
+        float p = L.p[mat + 2][row], m = L.m[mat + 2][row], v = L.v[mat + 2][row];
+        adam_zero_grad_steps(p, m, v, from, to, L);
+        L.p[mat + 2][row] = p; L.m[mat + 2][row] = m; L.v[mat + 2][row] = v;
+        L.g[mat + 2][row] = 0.f;
+    }
+}
+
+template <int G, typename IdT>
+__global__ void __launch_bounds__(256) lazy_prepare_kernel(const LazyState L, const void* users, const void* items, int64_t B,
+                                                           int N, int M, int K, int t) {
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1);
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (gid >= B) return;
+    const int64_t u = (int64_t)((const IdT*)users)[gid], it = (int64_t)((const IdT*)items)[gid];
+    if (u < 0 || u >= N || it < 0 || it >= M) return;   // reported by the gradient kernel
+    int first_u = 0, first_i = 0;
+    if (gl == 0) {
+        first_u = atomicMax(L.claim_user + u, t) < t;    // first group of this step to see the row owns its catch-up
+        first_i = atomicMax(L.claim_item + it, t) < t;
+    }
+    first_u = __shfl_sync(gmask, first_u, lane & ~(G - 1));
+    first_i = __shfl_sync(gmask, first_i, lane & ~(G - 1));
+    if (first_u) {
+        lazy_catch_up_row<G>(L, 0, u, K, t, gl, L.last_user);
+        if (gl == 0) L.touched_user[atomicAdd(L.counters + 0, 1)] = (int32_t)u;
+    }
+    if (first_i) {
+        lazy_catch_up_row<G>(L, 1, it, K, t, gl, L.last_item);
+        if (gl == 0) L.touched_item[atomicAdd(L.counters + 1, 1)] = (int32_t)it;
+    }
+}
+
+// the touched rows take step t with their accumulated gradient
+template <int G>
+__global__ void __launch_bounds__(256) lazy_update_kernel(const LazyState L, int K, int t) {
+    const int gl = threadIdx.x & (G - 1);
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int nu = L.counters[0], ni = L.counters[1];
+    if (gid >= nu + ni) return;
+    const int mat = gid < nu ? 0 : 1;
+    const int64_t row = mat == 0 ? L.touched_user[gid] : L.touched_item[gid - nu];
+    for (int k = gl; k < K; k += G) {
+        const size_t e = (size_t)row * K + k;
+        float p = L.p[mat][e], m = L.m[mat][e], v = L.v[mat][e];
+        adam_one_step(p, m, v, L.g[mat][e], t, L);
+        L.p[mat][e] = p; L.m[mat][e] = m; L.v[mat][e] = v;
+    }
+    if (gl == 0) {
+        float p = L.p[mat + 2][row], m = L.m[mat + 2][row], v = L.v[mat + 2][row];
+        adam_one_step(p, m, v, L.g[mat + 2][row], t, L);
+        L.p[mat + 2][row] = p; L.m[mat + 2][row] = m; L.v[mat + 2][row] = v;
+        (mat == 0 ? L.last_user : L.last_item)[row] = t;
+    }
+}
+
+// bring every row up to step t (end of training / before the parameters are read from outside)
+__global__ void __launch_bounds__(256) lazy_flush_kernel(const LazyState L, int N, int M, int K, int t) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= (int64_t)N + M) return;
+    const int mat = wid < N ? 0 : 1;
+    const int64_t row = mat == 0 ? wid : wid - N;
+    int32_t* last = mat == 0 ? L.last_user : L.last_item;
+    const int from = last[row] + 1;
+    if (from > t) return;
+    for (int k = lane; k < K; k += 32) {
+        const size_t e = (size_t)row * K + k;
+        float p = L.p[mat][e], m = L.m[mat][e], v = L.v[mat][e];
+        adam_zero_grad_steps(p, m, v, from, t, L);
+        L.p[mat][e] = p; L.m[mat][e] = m; L.v[mat][e] = v;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        float p = L.p[mat + 2][row], m = L.m[mat + 2][row], v = L.v[mat + 2][row];
+        adam_zero_grad_steps(p, m, v, from, t, L);
+        L.p[mat + 2][row] = p; L.m[mat + 2][row] = m; L.v[mat + 2][row] = v;
+        last[row] = t;
+    }
+}
+
 }  // namespace pmf
 
 using namespace pmf;
@@ -207,6 +333,80 @@ int pmf_hpf_map_predict(const void* d_users, const void* d_items, int32_t id_byt
     const unsigned grid = (unsigned)cdiv(n * 32, 256);
     if (id_bytes == 8) hpf_map_predict_kernel<int64_t><<<grid, 256, 0, (cudaStream_t)stream>>>(d_users, d_items, n, d_theta_raw, d_beta_raw, N, M, K, d_out);
     else hpf_map_predict_kernel<int32_t><<<grid, 256, 0, (cudaStream_t)stream>>>(d_users, d_items, n, d_theta_raw, d_beta_raw, N, M, K, d_out);
+    PMF_LAUNCH_CHECK();
+    return PMF_OK;
+}
+
+
+static int lazy_state_from(const pmf_lazy_adam* st, LazyState& L) {
+    PMF_REQUIRE(st != nullptr, "state is NULL");
+    const float* const* groups[4] = {nullptr, nullptr, nullptr, nullptr};
+    (void)groups;
+    float* const P[4] = {st->theta, st->beta, st->xi, st->eta};
+    float* const Mo[4] = {st->m_theta, st->m_beta, st->m_xi, st->m_eta};
+    float* const Vo[4] = {st->v_theta, st->v_beta, st->v_xi, st->v_eta};
+    float* const Gr[4] = {st->g_theta, st->g_beta, st->g_xi, st->g_eta};
+    for (int k = 0; k < 4; ++k) {
+        PMF_REQUIRE(P[k] && Mo[k] && Vo[k] && Gr[k], "NULL parameter / moment / gradient tensor");
+        L.p[k] = P[k]; L.m[k] = Mo[k]; L.v[k] = Vo[k]; L.g[k] = Gr[k];
+    }
+    PMF_REQUIRE(st->last_user && st->last_item && st->claim_user && st->claim_item && st->touched_user &&
+                    st->touched_item && st->counters && st->step_size && st->bc2_sqrt, "NULL bookkeeping array");
+    L.last_user = st->last_user; L.last_item = st->last_item; L.claim_user = st->claim_user; L.claim_item = st->claim_item;
+    L.touched_user = st->touched_user; L.touched_item = st->touched_item; L.counters = st->counters;
+    L.step_size = st->step_size; L.bc2_sqrt = st->bc2_sqrt;
+    L.beta1 = st->beta1; L.beta2 = st->beta2; L.eps = st->eps;
+    return PMF_OK;
+}
+
+int pmf_hpf_map_lazy_epoch(const pmf_lazy_adam* st, const void* d_users, const void* d_items, int32_t id_bytes,
+                           const float* d_ratings, int64_t n, int64_t batch, int64_t step0, const float* d_user_scale,
+                           const float* d_item_scale, int32_t N, int32_t M, int32_t K, float a, float a_prime,
+                           float b_prime, float c, float c_prime, float d_prime, double* d_loss, int32_t* d_bad,
+                           void* stream) {
+    LazyState L;
+    PMF_TRY(lazy_state_from(st, L));
+    PMF_REQUIRE(n >= 0 && batch >= 1 && step0 >= 0, "bad sizes");
+    PMF_REQUIRE(id_bytes == 4 || id_bytes == 8, "id_bytes must be 4 or 8");
+    PMF_REQUIRE(K >= 1 && K <= 256, "K=%d outside [1, 256]", K);
+    PMF_REQUIRE(d_user_scale && d_item_scale && d_loss && d_bad, "NULL argument");
+    if (n == 0) return PMF_OK;
+    PMF_REQUIRE(d_users && d_items && d_ratings, "NULL batch");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int G = K <= 64 ? 8 : 32;
+    int64_t t = step0;
+    for (int64_t off = 0; off < n; off += batch) {
+        const int64_t B = (n - off) < batch ? (n - off) : batch;
+        ++t;
+        PMF_REQUIRE(t < INT32_MAX, "too many steps");
+        const void* u = (const char*)d_users + off * id_bytes;
+        const void* it = (const char*)d_items + off * id_bytes;
+        PMF_CUDA(cudaMemsetAsync(L.counters, 0, 2 * sizeof(int32_t), s));
+        const unsigned grid = (unsigned)cdiv(B * G, 256);
+        if (G == 8) {
+            if (id_bytes == 8) lazy_prepare_kernel<8, int64_t><<<grid, 256, 0, s>>>(L, u, it, B, N, M, K, (int)t);
+            else lazy_prepare_kernel<8, int32_t><<<grid, 256, 0, s>>>(L, u, it, B, N, M, K, (int)t);
+        } else {
+            if (id_bytes == 8) lazy_prepare_kernel<32, int64_t><<<grid, 256, 0, s>>>(L, u, it, B, N, M, K, (int)t);
+            else lazy_prepare_kernel<32, int32_t><<<grid, 256, 0, s>>>(L, u, it, B, N, M, K, (int)t);
+        }
+        PMF_LAUNCH_CHECK();
+        PMF_TRY(pmf_hpf_map_loss_grad(u, it, id_bytes, d_ratings + off, B, st->theta, st->beta, st->xi, st->eta, d_user_scale,
+                                      d_item_scale, N, M, K, a, a_prime, b_prime, c, c_prime, d_prime, st->g_theta,
+                                      st->g_beta, st->g_xi, st->g_eta, d_loss, d_bad, stream));
+        const unsigned ugrid = (unsigned)cdiv(2 * B * G, 256);   // at most B touched rows per side
+        if (G == 8) lazy_update_kernel<8><<<ugrid, 256, 0, s>>>(L, K, (int)t);
+        else lazy_update_kernel<32><<<ugrid, 256, 0, s>>>(L, K, (int)t);
+        PMF_LAUNCH_CHECK();
+    }
+    return PMF_OK;
+}
+
+int pmf_hpf_map_lazy_flush(const pmf_lazy_adam* st, int32_t N, int32_t M, int32_t K, int64_t step_now, void* stream) {
+    LazyState L;
+    PMF_TRY(lazy_state_from(st, L));
+    PMF_REQUIRE(step_now >= 0 && step_now < INT32_MAX, "bad step");
+    lazy_flush_kernel<<<(unsigned)cdiv(((int64_t)N + M) * 32, 256), 256, 0, (cudaStream_t)stream>>>(L, N, M, K, (int)step_now);
     PMF_LAUNCH_CHECK();
     return PMF_OK;
 }

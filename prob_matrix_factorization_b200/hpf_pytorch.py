@@ -143,15 +143,18 @@ class HPF_PyTorch(nn.Module):
             raise IndexError("index out of range in HPF_PyTorch batch")
 
     # -- loader-free training ------------------------------------------------------------------------
-    def fit_epochs(self, users, items, ratings, epochs=None, batch_size=4096, lr=None, shuffle=True, on_epoch=None):
+    def fit_epochs(self, users, items, ratings, epochs=None, batch_size=4096, lr=None, shuffle=True, on_epoch=None,
+                   lazy=True):
         """The scripts' loop (compare_models.py:299-313) without the DataLoader.
 
         Per epoch the shuffle is torch's own: ``DataLoader.__iter__`` draws ``_base_seed`` then
         ``RandomSampler`` draws its seed from the global CPU generator and calls
         ``torch.randperm(n, generator=Generator().manual_seed(seed))`` -- replayed here bit for bit, so a
         run under the same ``torch.manual_seed`` visits the same mini-batches as the reference loop.
-        Each step = one fused loss+gradient kernel and one fused dense Adam kernel per tensor.
-        Returns the list of epoch losses (sum of mini-batch losses, as the scripts print).
+        ``lazy=True`` (default): touch-only Adam -- rows without gradient are replayed in registers when next
+        touched (``pmf_hpf_map_lazy_epoch``; same arithmetic as the dense update, the whole epoch is enqueued
+        by one C call).  ``lazy=False``: one fused loss+gradient kernel and one dense Adam kernel per tensor per
+        step.  Returns the list of epoch losses (sum of mini-batch losses, as the scripts print).
         """
         cfg = self.config
         epochs = cfg.epochs if epochs is None else epochs
@@ -164,9 +167,12 @@ class HPF_PyTorch(nn.Module):
         if self._adam is None:
             self._adam = {"step": 0, "m": [torch.zeros_like(p) for p in params], "v": [torch.zeros_like(p) for p in params]}
         st = self._adam
-        grads = [torch.zeros_like(p) for p in params]
+        grads = st.setdefault("g", [torch.zeros_like(p) for p in params])
         beta1, beta2, eps = 0.9, 0.999, 1e-8
         losses = []
+        if lazy:
+            return self._fit_epochs_lazy(u_all, i_all, r_all, epochs, batch_size, lr, shuffle, on_epoch, st, params,
+                                         grads, (beta1, beta2, eps))
         with torch.cuda.device(dev), torch.no_grad():
             for ep in range(epochs):
                 if shuffle:
@@ -196,3 +202,63 @@ class HPF_PyTorch(nn.Module):
                     on_epoch(ep, losses[-1])
         self.check_ids()
         return losses
+
+    def _fit_epochs_lazy(self, u_all, i_all, r_all, epochs, batch_size, lr, shuffle, on_epoch, st, params, grads, hyp):
+        import ctypes as C
+        beta1, beta2, eps = hyp
+        cfg, dev, n = self.config, self.theta_uncons.device, u_all.numel()
+        steps_per_epoch = (n + batch_size - 1) // batch_size
+        total = st["step"] + epochs * steps_per_epoch
+        # per-step scalars exactly as torch computes them (float64 on the host, then float32)
+        s_idx = np.arange(total + 1, dtype=np.float64)
+        with np.errstate(divide="ignore"):
+            step_size = (lr / (1.0 - beta1 ** s_idx)).astype(np.float32)
+        bc2 = np.sqrt(1.0 - beta2 ** s_idx).astype(np.float32)
+        step_size[0], bc2[0] = 0.0, 1.0
+        tab = (torch.from_numpy(step_size).to(dev), torch.from_numpy(bc2).to(dev))
+        i32 = lambda k: torch.zeros(k, dtype=torch.int32, device=dev)
+        if "last_user" not in st:
+            st.update(last_user=i32(self.n_users), last_item=i32(self.n_items), claim_user=i32(self.n_users),
+                      claim_item=i32(self.n_items))
+            st["last_user"].fill_(st["step"]); st["last_item"].fill_(st["step"])
+        touched = (i32(batch_size), i32(batch_size), i32(2))
+        S = _cabi.LazyAdamState()
+        for names, tensors in ((("theta", "beta", "xi", "eta"), params), (("m_theta", "m_beta", "m_xi", "m_eta"), st["m"]),
+                               (("v_theta", "v_beta", "v_xi", "v_eta"), st["v"]), (("g_theta", "g_beta", "g_xi", "g_eta"), grads)):
+            for nm, t in zip(names, tensors):
+                setattr(S, nm, t.data_ptr())
+        for nm, t in (("last_user", st["last_user"]), ("last_item", st["last_item"]), ("claim_user", st["claim_user"]),
+                      ("claim_item", st["claim_item"]), ("touched_user", touched[0]), ("touched_item", touched[1]),
+                      ("counters", touched[2]), ("step_size", tab[0]), ("bc2_sqrt", tab[1])):
+            setattr(S, nm, t.data_ptr())
+        S.beta1, S.beta2, S.eps = beta1, beta2, eps
+        losses = []
+        id_bytes = 8 if u_all.dtype == torch.int64 else 4
+        with torch.cuda.device(dev), torch.no_grad():
+            for ep in range(epochs):
+                if shuffle:
+                    _base_seed = torch.empty((), dtype=torch.int64).random_()          # dataloader.py _BaseDataLoaderIter
+                    seed = int(torch.empty((), dtype=torch.int64).random_().item())    # sampler.py RandomSampler.__iter__
+                    gen = torch.Generator()
+                    gen.manual_seed(seed)
+                    perm = torch.randperm(n, generator=gen).to(dev)
+                    u_ep, i_ep, r_ep = u_all[perm].contiguous(), i_all[perm].contiguous(), r_all[perm].contiguous()
+                else:
+                    u_ep, i_ep, r_ep = u_all, i_all, r_all
+                acc = torch.zeros((), dtype=torch.float64, device=dev)
+                _cabi.call("pmf_hpf_map_lazy_epoch", C.byref(S), u_ep.data_ptr(), i_ep.data_ptr(), id_bytes, r_ep.data_ptr(), n,
+                           batch_size, st["step"], self.user_scale.data_ptr(), self.item_scale.data_ptr(), self.n_users,
+                           self.n_items, self.K, cfg.a, cfg.a_prime, cfg.b_prime, cfg.c, cfg.c_prime, cfg.d_prime,
+                           acc.data_ptr(), self._bad.data_ptr(), _cabi.stream_ptr())
+                st["step"] += steps_per_epoch
+                losses.append(float(acc.item()))
+                if on_epoch is not None:
+                    self._lazy_flush(S, st)
+                    on_epoch(ep, losses[-1])
+            self._lazy_flush(S, st)
+        self.check_ids()
+        return losses
+
+    def _lazy_flush(self, S, st):
+        import ctypes as C
+        _cabi.call("pmf_hpf_map_lazy_flush", C.byref(S), self.n_users, self.n_items, self.K, st["step"], _cabi.stream_ptr())

@@ -73,10 +73,11 @@ def test_script_loop_unchanged(golden):
     assert rel_max(m.theta.detach().cpu().numpy(), np.logaddexp(0, g["final_theta"])) < 2e-5
 
 
-def test_fit_epochs_replays_the_loader(golden):
+@pytest.mark.parametrize("lazy", [False, True])
+def test_fit_epochs_replays_the_loader(golden, lazy):
     g = golden("hpf_pytorch")
     m = build(g)
-    losses = m.fit_epochs(g["u"], g["i"], g["x"], epochs=g["epochs"], batch_size=g["batch"], lr=g["lr"])
+    losses = m.fit_epochs(g["u"], g["i"], g["x"], epochs=g["epochs"], batch_size=g["batch"], lr=g["lr"], lazy=lazy)
     for ep in range(g["epochs"]):
         assert abs(losses[ep] - g["epoch_loss"][ep]) < 1e-5 * abs(g["epoch_loss"][ep])
     for k in P:
@@ -102,3 +103,28 @@ def test_wide_factors_and_out_of_range_ids():
     m.loss(torch.LongTensor([N + 3]), torch.LongTensor([0]), torch.FloatTensor([1.0]))
     with pytest.raises(IndexError):
         m.check_ids()
+
+
+def test_lazy_adam_equals_dense_adam():
+    """Touch-only Adam replays zero-gradient steps exactly: same parameters and moments as the dense kernel,
+    also across two fit_epochs calls and a switch between the two modes (tolerance covers only the float
+    atomics that combine duplicate ids inside a batch)."""
+    from prob_matrix_factorization_b200 import synth
+    from prob_matrix_factorization_b200.hpf_pytorch import HPF_PyTorch, HPF_PyTorch_Config
+    N, M, nnz, K = 3000, 2500, 20_000, 100
+    u, i, x = synth.make_ratings(N, M, nnz, seed=77)
+    uc = np.bincount(u, minlength=N); ic = np.bincount(i, minlength=M)
+    cfg = HPF_PyTorch_Config(n_factors=K, a=0.3, c=0.3, lr=0.01)
+    out = {}
+    for mode in ("dense", "lazy", "mixed"):
+        torch.manual_seed(11)
+        m = HPF_PyTorch(N, M, uc, ic, cfg)
+        l1 = m.fit_epochs(u, i, x + 1.0, epochs=2, batch_size=512, lr=0.01, lazy=mode != "dense")
+        l2 = m.fit_epochs(u, i, x + 1.0, epochs=1, batch_size=512, lr=0.01, lazy=mode == "lazy")
+        out[mode] = ([getattr(m, k + "_uncons").detach().cpu().numpy() for k in P], [t.cpu().numpy() for t in m._adam["m"]],
+                     [t.cpu().numpy() for t in m._adam["v"]], l1 + l2)
+    for mode in ("lazy", "mixed"):
+        for a, b in zip(out["dense"][:3], out[mode][:3]):
+            for x_, y_ in zip(a, b):
+                assert rel_max(y_, x_) < 1e-5, mode
+        assert np.allclose(out["dense"][3], out[mode][3], rtol=1e-6)
