@@ -144,17 +144,19 @@ class HPF_PyTorch(nn.Module):
 
     # -- loader-free training ------------------------------------------------------------------------
     def fit_epochs(self, users, items, ratings, epochs=None, batch_size=4096, lr=None, shuffle=True, on_epoch=None,
-                   lazy=True):
+                   lazy=False):
         """The scripts' loop (compare_models.py:299-313) without the DataLoader.
 
         Per epoch the shuffle is torch's own: ``DataLoader.__iter__`` draws ``_base_seed`` then
         ``RandomSampler`` draws its seed from the global CPU generator and calls
         ``torch.randperm(n, generator=Generator().manual_seed(seed))`` -- replayed here bit for bit, so a
         run under the same ``torch.manual_seed`` visits the same mini-batches as the reference loop.
-        ``lazy=True`` (default): touch-only Adam -- rows without gradient are replayed in registers when next
-        touched (``pmf_hpf_map_lazy_epoch``; same arithmetic as the dense update, the whole epoch is enqueued
-        by one C call).  ``lazy=False``: one fused loss+gradient kernel and one dense Adam kernel per tensor per
-        step.  Returns the list of epoch losses (sum of mini-batch losses, as the scripts print).
+        ``lazy=False`` (default): one fused loss+gradient kernel and one dense Adam kernel per tensor per step.
+        ``lazy=True``: touch-only Adam -- rows without gradient are replayed in registers when next touched
+        (``pmf_hpf_map_lazy_epoch``; same arithmetic as the dense update, the whole epoch is enqueued by one C
+        call).  It moves ~250x fewer bytes but is currently SLOWER at C4 (133 vs 97 ms/epoch, profiles/README.md):
+        the replay is a dependent chain of IEEE sqrt + divides per skipped step.  Returns the list of epoch
+        losses (sum of mini-batch losses, as the scripts print).
         """
         cfg = self.config
         epochs = cfg.epochs if epochs is None else epochs
