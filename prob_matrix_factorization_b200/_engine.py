@@ -206,22 +206,37 @@ class GammaEngine:
     # -- state upload --------------------------------------------------------------------------
     def load_means(self, E_theta, E_beta, E_xi=None, E_eta=None):
         """Upload the initial expectations (host float64, drawn by NumPy exactly as the reference)."""
-        self.E_theta.copy_(pad_table(E_theta, self.ld, self.dev))
-        self.E_beta.copy_(pad_table(E_beta, self.ld, self.dev))
+        if self.r.world > 1:
+            # identical host arrays on every rank: 1/world over PCIe each, the rest over NVLink
+            from .parallel import replicate_from_slices
+            for dst, host in ((self.E_theta, E_theta), (self.E_beta, E_beta)):
+                full = replicate_from_slices(np.asarray(host), self.dev, self.r.world, self.r.rank)
+                if full.shape[1] == self.ld and full.dtype == torch.float32:
+                    dst.copy_(full)
+                else:
+                    dst.zero_()
+                    dst[:, :full.shape[1]] = full
+        else:
+            self.E_theta.copy_(pad_table(E_theta, self.ld, self.dev))
+            self.E_beta.copy_(pad_table(E_beta, self.ld, self.dev))
         if self.hyper is not None:
             self.E_xi.copy_(to_device(np.asarray(E_xi, dtype=np.float32), self.dev))
             self.E_eta.copy_(to_device(np.asarray(E_eta, dtype=np.float32), self.dev))
 
-    def download_means(self, out_theta, out_beta):
-        """Copy E_theta / E_beta (first K columns) into caller-provided (pinned) float32 host tensors."""
+    def download_means(self, out_theta, out_beta, owned_only=False):
+        """Copy E_theta / E_beta (first K columns) into caller-provided (pinned) float32 host tensors.
+
+        ``owned_only`` (multi-GPU): copy just this rank's row ranges -- the replicas are identical, so the ranks'
+        owned rows together are the whole result.  Returns the number of bytes copied."""
         K = self.K
-        if self.ld == K:
-            out_theta.copy_(self.E_theta, non_blocking=True)
-            out_beta.copy_(self.E_beta, non_blocking=True)
-        else:
-            out_theta.copy_(self.E_theta[:, :K], non_blocking=True)
-            out_beta.copy_(self.E_beta[:, :K], non_blocking=True)
+        nbytes = 0
+        for out, tab, bounds in ((out_theta, self.E_theta, self.r.user_bounds), (out_beta, self.E_beta, self.r.item_bounds)):
+            lo, hi = (int(bounds[self.r.rank]), int(bounds[self.r.rank + 1])) if owned_only else (0, tab.shape[0])
+            src = tab[lo:hi] if self.ld == K else tab[lo:hi, :K]
+            out[lo:hi].copy_(src, non_blocking=True)
+            nbytes += (hi - lo) * K * 4
         torch.cuda.current_stream(self.dev).synchronize()
+        return nbytes
 
     # -- one pass ------------------------------------------------------------------------------
     def _pass(self, grouped, E_oth, E_self, shp, rte, shape_prior, rate_prior, rate_vec, hyper_rate, hyper_mean,

@@ -53,6 +53,22 @@ def balanced_row_bounds(row_ptr, parts):
     return bounds
 
 
+def replicate_from_slices(host, device, world, rank, dtype=None, group=None):
+    """Full device copy of a host array that every rank holds: each rank uploads only its 1/world slice over PCIe
+    and the slices are all-gathered over NVLink (instead of `world` full H2D copies through the same host)."""
+    n = int(host.shape[0])
+    per = (n + world - 1) // world
+    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+    src = host[lo:hi] if isinstance(host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(host[lo:hi]))
+    if dtype is not None and src.dtype != dtype:
+        src = src.to(dtype)
+    full = torch.empty((per * world,) + tuple(src.shape[1:]), dtype=src.dtype, device=device)
+    mine = full[rank * per:(rank + 1) * per]
+    mine[:hi - lo].copy_(src, non_blocking=True)
+    dist.all_gather_into_tensor(full, mine, group=group)
+    return full[:n]
+
+
 class RowExchange:
     """All-gather of each rank's owned row range of a replicated, row-major table (in place)."""
 

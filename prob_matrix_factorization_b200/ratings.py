@@ -140,14 +140,24 @@ class DeviceRatings:
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.device = device
         self.n_users, self.n_items = int(n_users), int(n_items)
-        u_d = to_device(u if isinstance(u, torch.Tensor) else as_id_array(u, "user"), device, torch.int32)
-        i_d = to_device(i if isinstance(i, torch.Tensor) else as_id_array(i, "item"), device, torch.int32)
-        x_d = to_device(x if isinstance(x, torch.Tensor) else np.asarray(x, dtype=np.float32), device, torch.float32)
+        self.rank, self.world = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
+        u_h = u if isinstance(u, torch.Tensor) else as_id_array(u, "user")
+        i_h = i if isinstance(i, torch.Tensor) else as_id_array(i, "item")
+        x_h = x if isinstance(x, torch.Tensor) else np.asarray(x, dtype=np.float32)
+        if self.world > 1 and not any(isinstance(t, torch.Tensor) and t.is_cuda for t in (u_h, i_h, x_h)):
+            # every rank holds the same host list: upload 1/world each, assemble over NVLink
+            from .parallel import replicate_from_slices
+            u_d = replicate_from_slices(u_h, device, self.world, self.rank, torch.int32)
+            i_d = replicate_from_slices(i_h, device, self.world, self.rank, torch.int32)
+            x_d = replicate_from_slices(x_h, device, self.world, self.rank, torch.float32)
+        else:
+            u_d = to_device(u_h, device, torch.int32)
+            i_d = to_device(i_h, device, torch.int32)
+            x_d = to_device(x_h, device, torch.float32)
         if not (u_d.numel() == i_d.numel() == x_d.numel()):
             raise ValueError("u, i, rating must have equal length")
         self.nnz = u_d.numel()
         self.h2d_bytes = self.nnz * 12
-        self.rank, self.world = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
         if seg_len is None:
             seg_len = auto_seg_len(self.nnz)
         with torch.cuda.device(device):
