@@ -7,6 +7,8 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
+import time
 
 import numpy as np
 import torch
@@ -16,6 +18,23 @@ from .parallel import PeerTable, RowExchange
 from .ratings import DeviceRatings, as_id_array, to_device
 
 MAX_DEVICE_LABELS = 64
+
+
+class Trace:
+    """PMF_TRACE=1: wall-clock of the phases of a fit on rank 0 (synchronises; diagnostics only)."""
+
+    on = bool(os.environ.get("PMF_TRACE"))
+
+    def __init__(self):
+        self.t = time.perf_counter()
+
+    def mark(self, what):
+        if Trace.on:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            if int(os.environ.get("RANK", 0)) == 0:
+                print(f"[pmf trace] {what}: {(now - self.t) * 1e3:.1f} ms", file=sys.stderr, flush=True)
+            self.t = now
 
 
 def row_stride(K):

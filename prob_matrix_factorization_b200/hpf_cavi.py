@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 from . import _cabi
-from ._engine import EvalSet, GammaEngine, eval_stats, normalise_ids, predict, table_to_host
+from ._engine import EvalSet, GammaEngine, Trace, eval_stats, normalise_ids, predict, table_to_host
 from .poisson_mf_cavi import _DeviceBacked
 from .ratings import DEFAULT_SEG_LEN, DeviceRatings, to_device
 
@@ -125,14 +125,19 @@ class HPF_CAVI(_DeviceBacked):
         if init is None:
             init = self._initial_state()
         self.gamma_a_xi, self.gamma_a_eta = init["gamma_a_xi"], init["gamma_a_eta"]
+        tr = Trace()
         if self._engine is not None:
             self._engine.close()          # collective on multi-GPU runs: every rank re-fits together
+        tr.mark("close previous engine")
         dr = DeviceRatings(user_ids, item_ids, ratings, self.n_users, self.n_items, self._device,
                            seg_len=self._seg_len, shard=self._shard)
+        tr.mark("ratings H2D + grouping + shard")
         hyper = {"user_shape": float(init["gamma_a_xi"]), "user_rate_prior": float(cfg.b_prime),
                  "item_shape": float(init["gamma_a_eta"]), "item_rate_prior": float(cfg.d_prime)}
         eng = GammaEngine(dr, cfg.n_factors, cfg.a, cfg.c, None, None, hyper=hyper)
+        tr.mark("engine tables (+ symmetric memory / IPC)")
         eng.load_means(init["E_theta"], init["E_beta"], init["E_xi"], init["E_eta"])
+        tr.mark("initial factors H2D")
         if self._allocation == "digamma" or self._track_elbo:
             eng.load_params(init["gamma_a_theta"], init["gamma_b_theta"], init["gamma_a_beta"], init["gamma_b_beta"],
                             init["gamma_b_xi"], init["gamma_b_eta"])
@@ -172,7 +177,9 @@ class HPF_CAVI(_DeviceBacked):
                             print("Early stopping.")
                         break
                 prev_val_rmse = val_rmse
+        tr.mark(f"{self.n_iter_} sweeps")
         eng.sync_params()
+        tr.mark("gather shape/rate tables")
         if self._auto_close:
             eng.close()                   # peer-mapped tables (multi-GPU) become ordinary device tensors
         if self.n_iter_ > 0:
