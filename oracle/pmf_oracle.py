@@ -498,9 +498,15 @@ def topn(F_user, F_item, n, user_rows=None):
     if user_rows is not None:
         Fu = Fu[user_rows]
     scores = np.zeros((Fu.shape[0], Fi.shape[0]), np.float32)
+    prod = np.empty_like(scores)
+    FiT = np.ascontiguousarray(Fi.T)
     for k in range(Fu.shape[1]):
-        prod = (Fu[:, k:k + 1] * Fi[None, :, k]).astype(np.float32)      # rounded product ...
-        scores = (scores + prod).astype(np.float32)                       # ... then rounded add (no FMA)
-    items = np.arange(Fi.shape[0])
-    idx = np.stack([np.lexsort((items, -row))[:n] for row in scores])     # score desc, then index asc
+        np.multiply(Fu[:, k:k + 1], FiT[k][None, :], out=prod)           # float32 product, rounded ...
+        np.add(scores, prod, out=scores)                                  # ... then rounded float32 add (no FMA)
+    M = Fi.shape[0]
+    idx = np.empty((Fu.shape[0], n), np.int64)
+    for b, row in enumerate(scores):
+        nth = np.partition(row, M - n)[M - n]                # n-th largest value: nothing below it can rank in the top n
+        cand = np.nonzero(row >= nth)[0]
+        idx[b] = cand[np.lexsort((cand, -row[cand]))[:n]]    # score desc, then index asc (== lexsort of the whole row)
     return idx.astype(np.int32), np.take_along_axis(scores, idx, axis=1)

@@ -75,6 +75,7 @@ _PROTOTYPES = {
                                          VP, VP, C.c_float, C.c_float, VP, VP]),
     "pmf_hpf_elbo": (C.c_int, [VP, C.c_int32, C.c_int32] + [VP] * 10 + [C.c_int32] * 4 + [C.c_float] * 6 + [VP, VP]),
     "pmf_topn_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "pmf_topn_workspace_bytes_ex": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "pmf_topn": (C.c_int, [VP, VP, C.c_int64, VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP,
                            C.c_int64, VP, VP]),
     "pmf_gauss_packed_stride": (C.c_int, [C.c_int]),

@@ -13,21 +13,9 @@
 //   exact path    topn_score_exact_kernel (CUDA cores, the exact chain) -> same select kernel.  Used when
 //                 tensor_cores == 0, and per row as fallback when a row's candidate set overflows.
 // Indices are therefore bit-exact against the oracle in both paths.
-#include <cuda_bf16.h>
-
-#include "common.cuh"
+#include "topn.cuh"
 
 namespace pmf {
-
-constexpr int kTile = 128;          // UMMA M = N = 128
-constexpr int kCandCap = 2048;      // candidates kept per row in shared memory
-constexpr int kSelThreads = 256;
-
-__device__ __forceinline__ float exact_dot(const float* __restrict__ u, const float* __restrict__ v, int K) {
-    float s = 0.f;
-    for (int k = 0; k < K; ++k) s = __fadd_rn(s, __fmul_rn(u[k], v[k]));   // no FMA contraction: matches the oracle
-    return s;
-}
 
 // ---------------------------------------------------------------------------------------------------
 // packing: fp32 rows -> bf16, UMMA K-major no-swizzle canonical tiles
@@ -69,32 +57,6 @@ __global__ void topn_maxnorm_kernel(const float* __restrict__ F, int64_t n_rows,
 // ---------------------------------------------------------------------------------------------------
 // tcgen05 scoring kernel
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok, spins = 0;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (!ok && ++spins > (1u << 22)) __trap();   // a lost arrival must surface as an error, never as a hung GPU
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-           (1ull << 46);
-}
-
 __global__ void __launch_bounds__(128) topn_mma_kernel(const __nv_bfloat16* __restrict__ A_pack,
                                                        const __nv_bfloat16* __restrict__ B_pack, int kp16,
                                                        float* __restrict__ S, int64_t m_padded) {
@@ -199,78 +161,9 @@ __global__ void __launch_bounds__(128) topn_score_exact_kernel(const float* __re
 // ---------------------------------------------------------------------------------------------------
 // selection: one CTA per user row
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned order_key(float v) {   // larger float <=> larger unsigned
-    const unsigned u = __float_as_uint(v);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-struct SelArgs {
-    float* S;
-    int64_t m_padded;
-    int32_t n_items, n, approx;
-    const float *F_user, *F_item;
-    const int32_t* rows;
-    int32_t K, ld;
-    const unsigned* item_maxnorm2_bits;
-    int32_t* idx_out;
-    float* score_out;
-    int32_t* stats;   // [0] rows re-scored exactly in full, [1] candidates re-scored (approx path)
-};
-
-// key of the n-th largest element of s[0..M) and how many of the elements equal to it belong to the top n
-__device__ void radix_select(const float* __restrict__ s, int M, int n, unsigned* hist, unsigned* sh, unsigned* key_out,
-                             int* need_eq_out) {
-    unsigned prefix = 0, mask = 0;
-    int remaining = n;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
-        __syncthreads();
-        for (int j = threadIdx.x; j < M; j += blockDim.x) {
-            const unsigned k = order_key(s[j]);
-            if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int acc = 0, d = 255;
-            for (; d >= 0; --d) {
-                if (acc + (int)hist[d] >= remaining) break;
-                acc += (int)hist[d];
-            }
-            sh[0] = (unsigned)d;
-            sh[1] = (unsigned)(remaining - acc);
-        }
-        __syncthreads();
-        prefix |= sh[0] << shift;
-        mask |= 255u << shift;
-        remaining = (int)sh[1];
-        __syncthreads();
-    }
-    *key_out = prefix;
-    *need_eq_out = remaining;
-}
-
-__device__ __forceinline__ bool ranks_before(float sa, int ia, float sb, int ib) { return sa > sb || (sa == sb && ia < ib); }
-
-__device__ void bitonic_sort(float* sc, int* ix, int n_pow2) {
-    for (int k = 2; k <= n_pow2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < n_pow2; t += blockDim.x) {
-                const int p = t ^ j;
-                if (p > t) {
-                    const bool up = (t & k) == 0;
-                    const bool swap = up ? ranks_before(sc[p], ix[p], sc[t], ix[t]) : ranks_before(sc[t], ix[t], sc[p], ix[p]);
-                    if (swap) {
-                        const float ts = sc[t]; sc[t] = sc[p]; sc[p] = ts;
-                        const int ti = ix[t]; ix[t] = ix[p]; ix[p] = ti;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kSelThreads) topn_select_kernel(const SelArgs a) {
+// Top n of one row from its score array s[0..n_items): approximate scores (approx: candidates re-scored exactly) or
+// exact ones.  score_first: fill s with exact scores before selecting (the fused path's fallback rows).
+__device__ void select_row(const SelArgs& a, int64_t row, float* __restrict__ s, bool approx, bool score_first) {
     __shared__ unsigned hist[256];
     __shared__ unsigned sh[4];
     __shared__ float c_score[kCandCap];
@@ -278,14 +171,16 @@ __global__ void __launch_bounds__(kSelThreads) topn_select_kernel(const SelArgs 
     __shared__ int s_count, s_eq_taken;
     __shared__ int warp_cnt[kSelThreads / 32];
     extern __shared__ float s_user[];   // [K]
-    const int64_t row = blockIdx.x;
-    float* s = a.S + (size_t)row * a.m_padded;
     const int M = a.n_items, n = a.n;
     const float* urow = a.F_user + (size_t)(a.rows ? a.rows[row] : row) * a.ld;
     float un2 = 0.f;
     for (int k = threadIdx.x; k < a.K; k += blockDim.x) s_user[k] = urow[k];
     __syncthreads();
-    bool approx = a.approx != 0;
+    if (score_first) {
+        for (int j = threadIdx.x; j < M; j += blockDim.x) s[j] = exact_dot(s_user, a.F_item + (size_t)j * a.ld, a.K);
+        if (threadIdx.x == 0 && a.stats) atomicAdd(a.stats + 0, 1);
+        __syncthreads();
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
         unsigned key_n;
         int need_eq;
@@ -371,6 +266,41 @@ __global__ void __launch_bounds__(kSelThreads) topn_select_kernel(const SelArgs 
         a.idx_out[(size_t)row * n + t] = c_idx[t];
         a.score_out[(size_t)row * n + t] = c_score[t];
     }
+    __syncthreads();   // the shared buffers are reused by the caller's next row
+}
+
+__global__ void __launch_bounds__(kSelThreads) topn_select_kernel(const SelArgs a) {
+    const int64_t row = blockIdx.x;
+    select_row(a, row, a.S + (size_t)row * a.m_padded, a.approx != 0, false);
+}
+
+__global__ void __launch_bounds__(kSelThreads) topn_fallback_kernel(const SelArgs a, const int32_t* __restrict__ row_list,
+                                                                    const int32_t* __restrict__ row_count,
+                                                                    float* __restrict__ scratch) {
+    const int count = *row_count;
+    for (int i = blockIdx.x; i < count; i += gridDim.x)
+        select_row(a, row_list[i], scratch + (size_t)blockIdx.x * a.m_padded, false, true);
+}
+
+// host-side launchers used by topn_fused.cu
+int topn_launch_pack(const float* F, const int32_t* rows, int64_t n_rows, int64_t n_rows_padded, int K, int ld, int kp16,
+                     __nv_bfloat16* out, cudaStream_t s) {
+    const int kcs = kp16 / 8;
+    topn_pack_kernel<<<(unsigned)cdiv(n_rows_padded * kcs, 256), 256, 0, s>>>(F, rows, n_rows, n_rows_padded, K, ld, kp16, out);
+    PMF_LAUNCH_CHECK();
+    return PMF_OK;
+}
+int topn_launch_maxnorm(const float* F, int64_t n_rows, int K, int ld, unsigned* out_bits, cudaStream_t s) {
+    PMF_CUDA(cudaMemsetAsync(out_bits, 0, sizeof(unsigned), s));
+    topn_maxnorm_kernel<<<(unsigned)cdiv(n_rows * 32, 256), 256, 0, s>>>(F, n_rows, K, ld, out_bits);
+    PMF_LAUNCH_CHECK();
+    return PMF_OK;
+}
+int topn_launch_fallback(const SelArgs& a, const int32_t* row_list, const int32_t* row_count, float* scratch, int n_ctas,
+                         cudaStream_t s) {
+    topn_fallback_kernel<<<(unsigned)n_ctas, kSelThreads, (size_t)a.K * sizeof(float), s>>>(a, row_list, row_count, scratch);
+    PMF_LAUNCH_CHECK();
+    return PMF_OK;
 }
 
 }  // namespace pmf
@@ -381,10 +311,25 @@ extern "C" {
 
 static int64_t pad_to(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
-int64_t pmf_topn_workspace_bytes(int64_t batch_rows, int32_t n_items, int32_t K) {
-    if (batch_rows <= 0 || n_items <= 0 || K <= 0) return -1;
+static int64_t unfused_workspace_bytes(int64_t batch_rows, int32_t n_items, int32_t K) {
     const int64_t bp = pad_to(batch_rows, kTile), mp = pad_to(n_items, kTile), kp16 = pad_to(K, 16);
     return bp * mp * 4 + (bp + mp) * kp16 * 2 + 256;
+}
+
+// tensor_cores: 0 exact CUDA-core scoring, 1 tcgen05 (fused filter when the shape allows it), 2 tcgen05 unfused
+// (score matrix through HBM; kept as the comparison point)
+static bool use_fused(int32_t K, int32_t n, int32_t tensor_cores) { return tensor_cores == 1 && topn_fused_supported(K, n); }
+
+int64_t pmf_topn_workspace_bytes_ex(int64_t batch_rows, int32_t n_items, int32_t K, int32_t n, int32_t tensor_cores) {
+    if (batch_rows <= 0 || n_items <= 0 || K <= 0 || n <= 0) return -1;
+    if (use_fused(K, n, tensor_cores)) return topn_fused_workspace_bytes(batch_rows, n_items, K);
+    return unfused_workspace_bytes(batch_rows, n_items, K);
+}
+
+int64_t pmf_topn_workspace_bytes(int64_t batch_rows, int32_t n_items, int32_t K) {   // enough for every mode and n
+    if (batch_rows <= 0 || n_items <= 0 || K <= 0) return -1;
+    const int64_t a = unfused_workspace_bytes(batch_rows, n_items, K), b = topn_fused_workspace_bytes(batch_rows, n_items, K);
+    return a > b ? a : b;
 }
 
 int pmf_topn(const float* d_F_user, const int32_t* d_user_rows, int64_t batch_rows, const float* d_F_item,
@@ -392,11 +337,19 @@ int pmf_topn(const float* d_F_user, const int32_t* d_user_rows, int64_t batch_ro
              void* d_workspace, int64_t workspace_bytes, int32_t* d_stats, void* stream) {
     PMF_REQUIRE(batch_rows >= 0 && n_items > 0 && K >= 1 && ld >= K, "bad shape");
     PMF_REQUIRE(n >= 1 && n <= n_items && n <= kCandCap / 2, "n=%d must lie in [1, min(n_items, %d)]", n, kCandCap / 2);
+    PMF_REQUIRE(tensor_cores >= 0 && tensor_cores <= 2, "tensor_cores must be 0, 1 or 2");
     if (batch_rows == 0) return PMF_OK;
     PMF_REQUIRE(d_F_user && d_F_item && d_idx && d_score && d_workspace, "NULL argument");
-    PMF_REQUIRE(workspace_bytes >= pmf_topn_workspace_bytes(batch_rows, n_items, K), "workspace too small");
+    PMF_REQUIRE(workspace_bytes >= pmf_topn_workspace_bytes_ex(batch_rows, n_items, K, n, tensor_cores),
+                "workspace too small: %lld < %lld bytes", (long long)workspace_bytes,
+                (long long)pmf_topn_workspace_bytes_ex(batch_rows, n_items, K, n, tensor_cores));
     PMF_REQUIRE(K <= 512, "K=%d too wide for top-n scoring", K);
     cudaStream_t s = (cudaStream_t)stream;
+    if (d_stats) PMF_CUDA(cudaMemsetAsync(d_stats, 0, 2 * sizeof(int32_t), s));
+    if (use_fused(K, n, tensor_cores)) {
+        TopnProblem p{d_F_user, d_user_rows, batch_rows, d_F_item, n_items, K, ld, n, d_idx, d_score, d_stats};
+        return topn_fused_run(p, d_workspace, workspace_bytes, s);
+    }
     const int64_t bp = pad_to(batch_rows, kTile), mp = pad_to(n_items, kTile);
     const int kp16 = (int)pad_to(K, 16);
     uint8_t* ws = (uint8_t*)d_workspace;
@@ -404,16 +357,10 @@ int pmf_topn(const float* d_F_user, const int32_t* d_user_rows, int64_t batch_ro
     __nv_bfloat16* A_pack = (__nv_bfloat16*)(ws + bp * mp * 4);
     __nv_bfloat16* B_pack = A_pack + bp * kp16;
     unsigned* maxnorm = (unsigned*)(B_pack + mp * kp16);
-    if (d_stats) PMF_CUDA(cudaMemsetAsync(d_stats, 0, 2 * sizeof(int32_t), s));
     if (tensor_cores) {
-        PMF_CUDA(cudaMemsetAsync(maxnorm, 0, sizeof(unsigned), s));
-        topn_maxnorm_kernel<<<(unsigned)cdiv((int64_t)n_items * 32, 256), 256, 0, s>>>(d_F_item, n_items, K, ld, maxnorm);
-        PMF_LAUNCH_CHECK();
-        const int kcs = kp16 / 8;
-        topn_pack_kernel<<<(unsigned)cdiv(bp * kcs, 256), 256, 0, s>>>(d_F_user, d_user_rows, batch_rows, bp, K, ld, kp16, A_pack);
-        PMF_LAUNCH_CHECK();
-        topn_pack_kernel<<<(unsigned)cdiv(mp * kcs, 256), 256, 0, s>>>(d_F_item, nullptr, n_items, mp, K, ld, kp16, B_pack);
-        PMF_LAUNCH_CHECK();
+        PMF_TRY(topn_launch_maxnorm(d_F_item, n_items, K, ld, maxnorm, s));
+        PMF_TRY(topn_launch_pack(d_F_user, d_user_rows, batch_rows, bp, K, ld, kp16, A_pack, s));
+        PMF_TRY(topn_launch_pack(d_F_item, nullptr, n_items, mp, K, ld, kp16, B_pack, s));
         const size_t smem = (size_t)2 * kTile * kp16 * 2;
         PMF_REQUIRE(smem <= 200 * 1024, "K=%d needs %zu bytes of shared memory per tile pair", K, smem);
         PMF_CUDA(cudaFuncSetAttribute(topn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,0 +1,432 @@
+// a11: dense U V^T top-n scoring, fused form -- the score matrix never reaches HBM.
+//
+// The unfused pipeline in topn.cu writes batch x n_items approximate scores (1.8 GB for 2048 x 230k) and reads them
+// back five times to select; its tensor pipe idles waiting for those stores.  Here the MMA epilogue tests every score
+// against a per-row threshold while it is still in registers and only the survivors (a few hundred per row) are kept:
+//
+//   level 0   the first kLevel0Tiles item tiles are scored with no threshold ("dense": every score kept, <= kFuseCap/2)
+//   refine    per row: t = n-th largest approximate score so far.  The n-th largest over ALL items can only be larger,
+//             so an item scoring below t - 2*margin can never be needed (margin bounds the bf16 error, see topn.cu);
+//             the list is compacted to the entries above that threshold
+//   level l   the next item range (g times what has been covered, g ~ 1024/n) is scored against the thresholds;
+//             expected survivors per row ~ n*g, far below the list capacity
+//   finish    after the last level the list holds every item with S~ >= t - 2*margin >= (true n-th S~) - 2*margin, i.e.
+//             exactly the candidate set the unfused path proves sufficient: exact fp32 re-score, sort, write the top n
+//   fallback  rows whose list overflowed (massive ties) are scored exactly in full by topn_fallback_kernel; the list of
+//             such rows lives on the device, so there is no host synchronisation anywhere
+//
+// topn_filter_kernel is a persistent warp-specialised tcgen05 kernel, one CTA per SM:
+//   warp 0        producer: cp.async.bulk of the two 128-row user tiles of a work unit, then a ring of item tiles
+//   warp 1        one thread issues tcgen05.mma 128x128x16 (bf16 -> fp32 in TMEM): each item tile is multiplied with
+//                 BOTH user tiles, so every byte of B fetched from L2 feeds 256 rows (L2 read rate 32 B/clk/SM, under
+//                 the ~42 B/clk/SM the L2 sustains chip-wide); two accumulator stages x two row blocks = 512 TMEM columns
+//   warps 2..9    epilogue: warp w drains TMEM lanes 32*(w%4).. of row block (w-2)/4 with tcgen05.ld.x32, takes the
+//                 running maximum of 32 scores and only on a hit walks them to append (item, score) to the row's list
+#include "topn.cuh"
+
+namespace pmf {
+
+constexpr int kFuseCap = 4096;                 // list capacity per row
+constexpr int kLevel0Tiles = kFuseCap / 2 / kTile;   // 16 tiles = 2048 items scored densely
+constexpr int kFuseRows = 2 * kTile;           // user rows per CTA (two UMMA M = 128 row blocks)
+constexpr int kFuseThreads = 320;
+constexpr int kFuseMaxN = 256;                 // level 0 must hold several times n items
+constexpr int kMaxStages = 4;
+constexpr int kFallbackCtas = 148;
+constexpr size_t kFuseSmemBudget = 200 * 1024;
+
+struct FilterArgs {
+    const __nv_bfloat16 *A_pack, *B_pack;
+    int32_t kp16, stages;
+    int32_t n_rowpairs;                  // 256-row blocks of the batch
+    int32_t tile_begin, tile_end;        // item tiles of this level
+    int32_t tiles_per_unit, units_per_rowpair;
+    int32_t n_items, dense;
+    const float* thr;                    // [rows padded to 256]; +inf for padding rows and rows already overflowed
+    int32_t* cand_idx;
+    float* cand_score;                   // [rows][kFuseCap]
+    int32_t* cand_cnt;
+};
+
+__global__ void __launch_bounds__(kFuseThreads, 1) topn_filter_kernel(const FilterArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];   // A0 | A1 | B[stages]
+    __shared__ __align__(8) uint64_t bar_a_full, bar_a_empty, bar_b_full[kMaxStages], bar_b_empty[kMaxStages], bar_acc_full[2],
+        bar_acc_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+    const uint32_t tile_bytes = (uint32_t)kTile * a.kp16 * 2;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + 2 * tile_bytes;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stages = a.stages;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_a_full, 1);
+        mbar_init(&bar_a_empty, 1);
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&bar_b_full[i], 1); mbar_init(&bar_b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // all 512 TMEM columns: [stage][row block][128]
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+    const int total_units = a.n_rowpairs * a.units_per_rowpair;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t bs = 0, bphase = 0, ucount = 0;
+            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++ucount) {
+                const int rp = unit / a.units_per_rowpair, chunk = unit % a.units_per_rowpair;
+                const int t0 = a.tile_begin + chunk * a.tiles_per_unit;
+                const int t1 = min(t0 + a.tiles_per_unit, a.tile_end);
+                mbar_wait(&bar_a_empty, (ucount & 1u) ^ 1u);   // the previous unit's MMAs no longer read A
+                mbar_expect_tx(&bar_a_full, 2 * tile_bytes);
+                bulk_g2s(sA, reinterpret_cast<const uint8_t*>(a.A_pack) + (size_t)rp * 2 * tile_bytes, 2 * tile_bytes, &bar_a_full);
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(&bar_b_empty[bs], bphase ^ 1u);
+                    mbar_expect_tx(&bar_b_full[bs], tile_bytes);
+                    bulk_g2s(sB + (size_t)bs * tile_bytes, reinterpret_cast<const uint8_t*>(a.B_pack) + (size_t)t * tile_bytes,
+                             tile_bytes, &bar_b_full[bs]);
+                    if (++bs == (uint32_t)stages) { bs = 0; bphase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16_128x128();
+            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+            const int ksteps = a.kp16 / 16;
+            uint32_t bs = 0, bphase = 0, as = 0, aphase = 0, ucount = 0;
+            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++ucount) {
+                const int chunk = unit % a.units_per_rowpair;
+                const int t0 = a.tile_begin + chunk * a.tiles_per_unit;
+                const int t1 = min(t0 + a.tiles_per_unit, a.tile_end);
+                mbar_wait(&bar_a_full, ucount & 1u);
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(&bar_acc_empty[as], aphase ^ 1u);   // epilogue has drained this accumulator stage
+                    mbar_wait(&bar_b_full[bs], bphase);
+                    tc_fence_after();
+                    const uint32_t b_tile = b_base + bs * tile_bytes;
+#pragma unroll 1
+                    for (int rb = 0; rb < 2; ++rb) {
+                        const uint32_t d = tmem + as * 256u + (uint32_t)rb * 128u;
+                        const uint32_t a_tile = a_base + (uint32_t)rb * tile_bytes;
+                        for (int k = 0; k < ksteps; ++k)   // one MMA consumes K = 16 = two 8-wide k-chunks (LBO = 2048 B apart)
+                            umma_bf16(d, umma_desc(a_tile + (uint32_t)k * 4096u, 2048u, 128u),
+                                      umma_desc(b_tile + (uint32_t)k * 4096u, 2048u, 128u), idesc, k > 0);
+                    }
+                    umma_commit(&bar_b_empty[bs]);     // item tile consumed -> producer may refill the slot
+                    umma_commit(&bar_acc_full[as]);    // both accumulators of this stage complete -> epilogue
+                    if (++bs == (uint32_t)stages) { bs = 0; bphase ^= 1u; }
+                    if (++as == 2u) { as = 0; aphase ^= 1u; }
+                }
+                umma_commit(&bar_a_empty);             // every MMA of the unit done -> A tiles may be replaced
+            }
+        }
+    } else {
+        const int rb = (warp - 2) >> 2, q = warp & 3;   // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        const int cap = kFuseCap;
+        uint32_t as = 0, aphase = 0;
+        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+            const int rp = unit / a.units_per_rowpair, chunk = unit % a.units_per_rowpair;
+            const int t0 = a.tile_begin + chunk * a.tiles_per_unit;
+            const int t1 = min(t0 + a.tiles_per_unit, a.tile_end);
+            const int64_t row = (int64_t)rp * kFuseRows + rb * kTile + q * 32 + lane;
+            const float thr = a.thr[row];
+            int32_t* __restrict__ r_idx = a.cand_idx + (size_t)row * cap;
+            float* __restrict__ r_sc = a.cand_score + (size_t)row * cap;
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&bar_acc_full[as], aphase);
+                __syncwarp();
+                tc_fence_after();
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + as * 256u + (uint32_t)rb * 128u;
+#pragma unroll 1
+                for (int c0 = 0; c0 < kTile; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + (uint32_t)c0, r);
+                    const int item0 = t * kTile + c0;
+                    if (a.dense) {   // level 0: every score is kept, slot = position in the level
+                        const int slot0 = item0 - a.tile_begin * kTile;
+                        if (thr < INFINITY) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                *reinterpret_cast<uint4*>(r_sc + slot0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                                *reinterpret_cast<int4*>(r_idx + slot0 + j) = make_int4(item0 + j, item0 + j + 1, item0 + j + 2, item0 + j + 3);
+                            }
+                        }
+                    } else {
+                        float mx = __uint_as_float(r[0]);
+#pragma unroll
+                        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                        if (mx >= thr) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float v = __uint_as_float(r[j]);
+                                if (v >= thr && item0 + j < a.n_items) {
+                                    const int slot = atomicAdd(a.cand_cnt + row, 1);   // other CTAs append to the same row
+                                    if (slot < cap) { r_idx[slot] = item0 + j; r_sc[slot] = v; }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_acc_empty[as]);
+                if (++as == 2u) { as = 0; aphase ^= 1u; }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-row list maintenance
+// ---------------------------------------------------------------------------------------------------
+__global__ void topn_fused_init_kernel(float* thr, int32_t* cnt, int32_t* ovf_count, int64_t rows, int64_t rows_padded, int32_t cnt0) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) *ovf_count = 0;
+    if (r >= rows_padded) return;
+    thr[r] = r < rows ? -INFINITY : INFINITY;
+    cnt[r] = r < rows ? cnt0 : 0;
+}
+
+struct RefineArgs {
+    int32_t* cand_idx;
+    float* cand_score;
+    int32_t* cand_cnt;
+    float* thr;
+    int32_t n, final_level;
+    const float *F_user, *F_item;
+    const int32_t* rows;
+    int32_t K, ld;
+    const unsigned* item_maxnorm2_bits;
+    int32_t* idx_out;
+    float* score_out;
+    int32_t* stats;
+    int32_t *ovf_list, *ovf_count;
+};
+
+// One CTA per user row.  Dynamic shared memory: list scores | list indices | kept scores | kept indices | user row.
+__global__ void __launch_bounds__(kSelThreads) topn_refine_kernel(const RefineArgs a) {
+    extern __shared__ __align__(16) uint8_t dyn[];
+    float* l_sc = reinterpret_cast<float*>(dyn);
+    int* l_ix = reinterpret_cast<int*>(l_sc + kFuseCap);
+    float* k_sc = reinterpret_cast<float*>(l_ix + kFuseCap);
+    int* k_ix = reinterpret_cast<int*>(k_sc + kCandCap);
+    float* s_user = reinterpret_cast<float*>(k_ix + kCandCap);
+    __shared__ unsigned hist[256];
+    __shared__ unsigned sh[4];
+    __shared__ int s_count;
+    const int64_t row = blockIdx.x;
+    const int n = a.n;
+    if (a.thr[row] == INFINITY) return;     // overflowed at an earlier level: already on the fallback list
+    const int c = a.cand_cnt[row];
+    int32_t* g_ix = a.cand_idx + (size_t)row * kFuseCap;
+    float* g_sc = a.cand_score + (size_t)row * kFuseCap;
+    // a list that overflowed, or (final level) one that cannot hold n entries, sends the row to exact scoring
+    bool bad = c > kFuseCap || (a.final_level && c < n);
+    if (!bad) {
+        const float* urow = a.F_user + (size_t)(a.rows ? a.rows[row] : row) * a.ld;
+        for (int k = threadIdx.x; k < a.K; k += blockDim.x) s_user[k] = urow[k];
+        for (int t = threadIdx.x; t < c; t += blockDim.x) { l_sc[t] = g_sc[t]; l_ix[t] = g_ix[t]; }
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();
+        float thr_new = -INFINITY;
+        if (c >= n) {
+            unsigned key_n;
+            int need_eq;
+            radix_select(l_sc, c, n, hist, sh, &key_n, &need_eq);
+            if (threadIdx.x == 0) {
+                float un2 = 0.f;
+                for (int k = 0; k < a.K; ++k) un2 = fmaf(s_user[k], s_user[k], un2);
+                sh[2] = __float_as_uint(sqrtf(un2));
+            }
+            __syncthreads();
+            // margin = 2^-7 |u| max|v| bounds |S~ - S| (bf16 operands, Cauchy-Schwarz); see topn.cu::select_row
+            const float margin = 0.0078125f * __uint_as_float(sh[2]) * sqrtf(__uint_as_float(*a.item_maxnorm2_bits));
+            thr_new = key_to_float(key_n) - 2.f * margin - 1e-30f;
+        }
+        if (!a.final_level) {
+            for (int t = threadIdx.x; t < c; t += blockDim.x) {
+                if (l_sc[t] >= thr_new) {
+                    const int slot = atomicAdd(&s_count, 1);
+                    g_sc[slot] = l_sc[t];
+                    g_ix[slot] = l_ix[t];
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) { a.cand_cnt[row] = s_count; a.thr[row] = thr_new; }
+            return;
+        }
+        for (int t = threadIdx.x; t < c; t += blockDim.x) {
+            if (l_sc[t] >= thr_new) {
+                const int slot = atomicAdd(&s_count, 1);
+                if (slot < kCandCap) k_ix[slot] = l_ix[t];
+            }
+        }
+        __syncthreads();
+        const int kept = s_count;
+        bad = kept > kCandCap || kept < n;
+        if (!bad) {
+            for (int t = threadIdx.x; t < kept; t += blockDim.x) k_sc[t] = exact_dot(s_user, a.F_item + (size_t)k_ix[t] * a.ld, a.K);
+            if (threadIdx.x == 0 && a.stats) atomicAdd(a.stats + 1, kept);
+            int p2 = 1;
+            while (p2 < kept) p2 <<= 1;
+            for (int t = kept + threadIdx.x; t < p2; t += blockDim.x) { k_sc[t] = -INFINITY; k_ix[t] = 0x7FFFFFFF; }
+            __syncthreads();
+            bitonic_sort(k_sc, k_ix, p2);
+            for (int t = threadIdx.x; t < n; t += blockDim.x) {
+                a.idx_out[(size_t)row * n + t] = k_ix[t];
+                a.score_out[(size_t)row * n + t] = k_sc[t];
+            }
+            return;
+        }
+    }
+    if (threadIdx.x == 0) {
+        a.ovf_list[atomicAdd(a.ovf_count, 1)] = (int32_t)row;
+        a.thr[row] = INFINITY;   // later levels append nothing for this row
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static int64_t pad_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+static int fused_stages(int kp16) {
+    const size_t tile = (size_t)kTile * kp16 * 2;
+    int s = (int)(kFuseSmemBudget / tile) - 2;
+    return s > kMaxStages ? kMaxStages : s;
+}
+
+bool topn_fused_supported(int32_t K, int32_t n) { return n <= kFuseMaxN && fused_stages((int)pad_up(K, 16)) >= 2; }
+
+struct FusedLayout {
+    int64_t bp, mp, kp16;
+    size_t off_A, off_B, off_idx, off_score, off_cnt, off_thr, off_ovf, off_misc, off_scratch, total;
+    int fallback_ctas;
+};
+
+static FusedLayout fused_layout(int64_t batch_rows, int32_t n_items, int32_t K) {
+    FusedLayout L;
+    L.bp = pad_up(batch_rows, kFuseRows);
+    L.mp = pad_up(n_items, kTile);
+    L.kp16 = pad_up(K, 16);
+    L.fallback_ctas = (int)(batch_rows < kFallbackCtas ? batch_rows : kFallbackCtas);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 255) / 256 * 256; return at; };
+    L.off_A = take((size_t)L.bp * L.kp16 * 2);
+    L.off_B = take((size_t)L.mp * L.kp16 * 2);
+    L.off_idx = take((size_t)L.bp * kFuseCap * 4);
+    L.off_score = take((size_t)L.bp * kFuseCap * 4);
+    L.off_cnt = take((size_t)L.bp * 4);
+    L.off_thr = take((size_t)L.bp * 4);
+    L.off_ovf = take((size_t)L.bp * 4);
+    L.off_misc = take(256);                                     // [0] item max |v|^2 bits, [1] overflow row count
+    L.off_scratch = take((size_t)L.fallback_ctas * L.mp * 4);   // exact score rows of the fallback kernel
+    L.total = o;
+    return L;
+}
+
+int64_t topn_fused_workspace_bytes(int64_t batch_rows, int32_t n_items, int32_t K) {
+    return (int64_t)fused_layout(batch_rows, n_items, K).total;
+}
+
+static int launch_filter(FilterArgs fa, int tile_begin, int tile_end, int dense, size_t smem, cudaStream_t s) {
+    fa.tile_begin = tile_begin;
+    fa.tile_end = tile_end;
+    fa.dense = dense;
+    const int tiles = tile_end - tile_begin;
+    // work unit = one 256-row block x tiles_per_unit item tiles; >= 24 tiles per unit amortise the 2-tile A load, and
+    // the unit count is kept near a multiple of the SM count so the static round-robin ends evenly
+    int upr = 1;
+    if ((int64_t)fa.n_rowpairs * tiles > (int64_t)kNumSMs * 24) {
+        const int64_t units = pad_up(cdiv((int64_t)fa.n_rowpairs * tiles, 32), kNumSMs);
+        upr = (int)cdiv(units, fa.n_rowpairs);
+    } else {
+        upr = (int)cdiv(kNumSMs, fa.n_rowpairs);
+    }
+    if (upr > tiles) upr = tiles;
+    fa.tiles_per_unit = (int)cdiv(tiles, upr);
+    fa.units_per_rowpair = (int)cdiv(tiles, fa.tiles_per_unit);
+    const int64_t total = (int64_t)fa.n_rowpairs * fa.units_per_rowpair;
+    const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);
+    topn_filter_kernel<<<grid, kFuseThreads, smem, s>>>(fa);
+    PMF_LAUNCH_CHECK();
+    return PMF_OK;
+}
+
+int topn_fused_run(const TopnProblem& p, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
+    const FusedLayout L = fused_layout(p.batch_rows, p.n_items, p.K);
+    PMF_REQUIRE((int64_t)L.total <= workspace_bytes, "workspace too small for the fused top-n path");
+    PMF_REQUIRE(((uintptr_t)workspace & 15) == 0, "top-n workspace must be 16-byte aligned");
+    uint8_t* ws = (uint8_t*)workspace;
+    __nv_bfloat16* A_pack = (__nv_bfloat16*)(ws + L.off_A);
+    __nv_bfloat16* B_pack = (__nv_bfloat16*)(ws + L.off_B);
+    int32_t* cand_idx = (int32_t*)(ws + L.off_idx);
+    float* cand_score = (float*)(ws + L.off_score);
+    int32_t* cand_cnt = (int32_t*)(ws + L.off_cnt);
+    float* thr = (float*)(ws + L.off_thr);
+    int32_t* ovf_list = (int32_t*)(ws + L.off_ovf);
+    unsigned* maxnorm = (unsigned*)(ws + L.off_misc);
+    int32_t* ovf_count = (int32_t*)(ws + L.off_misc) + 1;
+    float* scratch = (float*)(ws + L.off_scratch);
+    const int kp16 = (int)L.kp16;
+    const int tiles = (int)(L.mp / kTile);
+
+    PMF_TRY(topn_launch_maxnorm(p.F_item, p.n_items, p.K, p.ld, maxnorm, s));
+    PMF_TRY(topn_launch_pack(p.F_user, p.user_rows, p.batch_rows, L.bp, p.K, p.ld, kp16, A_pack, s));
+    PMF_TRY(topn_launch_pack(p.F_item, nullptr, p.n_items, L.mp, p.K, p.ld, kp16, B_pack, s));
+    const int level0_tiles = tiles < kLevel0Tiles ? tiles : kLevel0Tiles;
+    const int32_t cnt0 = (int32_t)((int64_t)level0_tiles * kTile < p.n_items ? (int64_t)level0_tiles * kTile : p.n_items);
+    topn_fused_init_kernel<<<(unsigned)cdiv(L.bp, 256), 256, 0, s>>>(thr, cand_cnt, ovf_count, p.batch_rows, L.bp, cnt0);
+    PMF_LAUNCH_CHECK();
+
+    const int stages = fused_stages(kp16);
+    const size_t smem = (size_t)(2 + stages) * kTile * kp16 * 2;
+    PMF_CUDA(cudaFuncSetAttribute(topn_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t refine_smem = (size_t)kFuseCap * 8 + (size_t)kCandCap * 8 + (size_t)p.K * 4;
+    PMF_CUDA(cudaFuncSetAttribute(topn_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)refine_smem));
+
+    FilterArgs fa;
+    fa.A_pack = A_pack; fa.B_pack = B_pack; fa.kp16 = kp16; fa.stages = stages;
+    fa.n_rowpairs = (int32_t)(L.bp / kFuseRows); fa.n_items = p.n_items;
+    fa.thr = thr; fa.cand_idx = cand_idx; fa.cand_score = cand_score; fa.cand_cnt = cand_cnt;
+    RefineArgs ra;
+    ra.cand_idx = cand_idx; ra.cand_score = cand_score; ra.cand_cnt = cand_cnt; ra.thr = thr; ra.n = p.n;
+    ra.F_user = p.F_user; ra.F_item = p.F_item; ra.rows = p.user_rows; ra.K = p.K; ra.ld = p.ld;
+    ra.item_maxnorm2_bits = maxnorm; ra.idx_out = p.idx_out; ra.score_out = p.score_out; ra.stats = p.stats;
+    ra.ovf_list = ovf_list; ra.ovf_count = ovf_count;
+
+    PMF_TRY(launch_filter(fa, 0, level0_tiles, 1, smem, s));
+    int covered = level0_tiles;
+    const int growth = 1024 / p.n < 2 ? 2 : 1024 / p.n;   // a level adds ~ n * growth entries per row
+    while (covered < tiles) {
+        ra.final_level = 0;
+        topn_refine_kernel<<<(unsigned)p.batch_rows, kSelThreads, refine_smem, s>>>(ra);
+        PMF_LAUNCH_CHECK();
+        const int64_t want = (int64_t)covered * (1 + growth);
+        const int next = (int)(want < tiles ? want : tiles);
+        PMF_TRY(launch_filter(fa, covered, next, 0, smem, s));
+        covered = next;
+    }
+    ra.final_level = 1;
+    topn_refine_kernel<<<(unsigned)p.batch_rows, kSelThreads, refine_smem, s>>>(ra);
+    PMF_LAUNCH_CHECK();
+
+    SelArgs sa;
+    sa.S = nullptr; sa.m_padded = L.mp; sa.n_items = p.n_items; sa.n = p.n; sa.approx = 0;
+    sa.F_user = p.F_user; sa.F_item = p.F_item; sa.rows = p.user_rows; sa.K = p.K; sa.ld = p.ld;
+    sa.item_maxnorm2_bits = maxnorm; sa.idx_out = p.idx_out; sa.score_out = p.score_out; sa.stats = p.stats;
+    return topn_launch_fallback(sa, ovf_list, ovf_count, scratch, L.fallback_ctas, s);
+}
+
+}  // namespace pmf

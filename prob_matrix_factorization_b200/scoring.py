@@ -26,13 +26,17 @@ def _as_table(F, device):
     return pad_table(F, row_stride(F.shape[1]), device), F.shape[1]
 
 
-def top_n(F_user, F_item, n=50, user_rows=None, tensor_cores=True, batch_rows=1024, device=None, return_stats=False):
+def top_n(F_user, F_item, n=50, user_rows=None, tensor_cores=True, batch_rows=None, device=None, return_stats=False):
     """Top-``n`` items for every row of ``F_user`` (or the rows listed in ``user_rows``).
 
     Returns ``(idx int32[B, n], score float32[B, n])`` as NumPy arrays.  ``tensor_cores=True`` scores with
     tcgen05 (bf16 operands) and re-scores a provably sufficient candidate set exactly, so the indices equal
-    the exact path's bit for bit.
+    the exact path's bit for bit; for n <= 256 and K <= 208 the scores are filtered in the MMA epilogue and
+    never written to HBM.  ``tensor_cores="unfused"`` keeps the score matrix in HBM (comparison point),
+    ``False`` scores exactly on CUDA cores.  ``batch_rows``: user rows per library call (default 8192 fused,
+    1024 otherwise -- the unfused modes need 4*n_items bytes of workspace per row).
     """
+    mode = 2 if tensor_cores == "unfused" else int(bool(tensor_cores))
     _cabi.require_cuda()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     Fu, K = _as_table(F_user, device)
@@ -51,8 +55,12 @@ def top_n(F_user, F_item, n=50, user_rows=None, tensor_cores=True, batch_rows=10
     stats_total = np.zeros(2, dtype=np.int64)
     stats = torch.zeros(2, dtype=torch.int32, device=device)
     lib = _cabi.load()
+    if batch_rows is None:
+        batch_rows = 8192 if lib.pmf_topn_workspace_bytes_ex(256, M, K, n, mode) < 256 * M * 4 else 1024
     chunk = max(128, min(int(batch_rows), max(B, 1)))
-    ws_bytes = lib.pmf_topn_workspace_bytes(chunk, M, K)
+    ws_bytes = lib.pmf_topn_workspace_bytes_ex(chunk, M, K, n, mode)
+    if ws_bytes < 0:
+        raise ValueError("bad top-n shape")
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     with torch.cuda.device(device):
         for s in range(0, B, chunk):
@@ -61,7 +69,7 @@ def top_n(F_user, F_item, n=50, user_rows=None, tensor_cores=True, batch_rows=10
                 base_ptr, rows_ptr = Fu.data_ptr(), rows[s:e].data_ptr()
             else:
                 base_ptr, rows_ptr = Fu[s:e].data_ptr(), None
-            _cabi.call("pmf_topn", base_ptr, rows_ptr, e - s, Fi.data_ptr(), M, K, ld, n, int(bool(tensor_cores)),
+            _cabi.call("pmf_topn", base_ptr, rows_ptr, e - s, Fi.data_ptr(), M, K, ld, n, mode,
                        idx[s:e].data_ptr(), score[s:e].data_ptr(), ws.data_ptr(), ws_bytes, stats.data_ptr(),
                        _cabi.stream_ptr())
             if return_stats:
