@@ -43,15 +43,25 @@ __global__ void topn_pack_kernel(const float* __restrict__ F, const int32_t* __r
     *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(v);
 }
 
-__global__ void topn_maxnorm_kernel(const float* __restrict__ F, int64_t n_rows, int K, int ld, unsigned* __restrict__ out_bits) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= n_rows) return;
-    float s = 0.f;
-    for (int k = lane; k < K; k += 32) { const float v = F[(size_t)row * ld + k]; s = fmaf(v, v, s); }
+__global__ void __launch_bounds__(256) topn_maxnorm_kernel(const float* __restrict__ F, int64_t n_rows, int K, int ld,
+                                                          unsigned* __restrict__ out_bits) {
+    __shared__ float warp_max[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float best = 0.f;
+    // one warp per row, grid-stride; non-negative floats order like their bit patterns, so one atomicMax per CTA
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n_rows; row += (int64_t)gridDim.x * 8) {
+        float s = 0.f;
+        for (int k = lane; k < K; k += 32) { const float v = F[(size_t)row * ld + k]; s = fmaf(v, v, s); }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) atomicMax(out_bits, __float_as_uint(s));   // non-negative floats order like their bit patterns
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        best = fmaxf(best, s);
+    }
+    if (lane == 0) warp_max[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) best = fmaxf(best, warp_max[w]);
+        atomicMax(out_bits, __float_as_uint(best));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -292,7 +302,8 @@ int topn_launch_pack(const float* F, const int32_t* rows, int64_t n_rows, int64_
 }
 int topn_launch_maxnorm(const float* F, int64_t n_rows, int K, int ld, unsigned* out_bits, cudaStream_t s) {
     PMF_CUDA(cudaMemsetAsync(out_bits, 0, sizeof(unsigned), s));
-    topn_maxnorm_kernel<<<(unsigned)cdiv(n_rows * 32, 256), 256, 0, s>>>(F, n_rows, K, ld, out_bits);
+    const int64_t ctas = cdiv(n_rows, 8);
+    topn_maxnorm_kernel<<<(unsigned)(ctas < 8 * kNumSMs ? ctas : 8 * kNumSMs), 256, 0, s>>>(F, n_rows, K, ld, out_bits);
     PMF_LAUNCH_CHECK();
     return PMF_OK;
 }

@@ -40,6 +40,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (!ok && ++spins > (1u << 22)) __trap();   // a lost arrival must surface as an error, never as a hung GPU
     } while (!ok);
 }
+// Same, for the long waits of a persistent pipeline: the hardware may keep the warp suspended for up to ~1 us per try
+// instead of returning at once, so waiting warps do not eat the issue slots of the warps they are waiting for.
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(1000u) : "memory");
+        if (!ok && ++spins > (1u << 21)) __trap();
+    } while (!ok);
+}
+__device__ __forceinline__ bool elect_one() {   // true in exactly one lane of a converged warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -100,7 +115,8 @@ struct SelArgs {
     int32_t* stats;   // [0] rows re-scored exactly in full, [1] candidates re-scored (approx path)
 };
 
-// key of the n-th largest element of s[0..M) and how many of the elements equal to it belong to the top n
+// key of the n-th largest element of s[0..M) and how many of the elements equal to it belong to the top n.
+// hist: 256 counters, sh: 2 words, both shared; blockDim.x >= 32.
 __device__ inline void radix_select(const float* __restrict__ s, int M, int n, unsigned* hist, unsigned* sh, unsigned* key_out,
                                     int* need_eq_out) {
     unsigned prefix = 0, mask = 0;
@@ -108,19 +124,43 @@ __device__ inline void radix_select(const float* __restrict__ s, int M, int n, u
     for (int shift = 24; shift >= 0; shift -= 8) {
         for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
         __syncthreads();
-        for (int j = threadIdx.x; j < M; j += blockDim.x) {
-            const unsigned k = order_key(s[j]);
-            if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+        for (int j0 = 0; j0 < M; j0 += blockDim.x) {   // uniform trip count: the warp votes below
+            const int j = j0 + threadIdx.x;
+            unsigned digit = 256u;                      // 256 = not a candidate for this pass
+            if (j < M) {
+                const unsigned k = order_key(s[j]);
+                if ((k & mask) == prefix) digit = (k >> shift) & 255u;
+            }
+            // scores of one row share their leading bytes, so most lanes want the same counter: one atomic per distinct
+            // digit per warp instead of a 32-way same-address conflict
+            const unsigned peers = __match_any_sync(0xffffffffu, digit);
+            if (digit != 256u && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned)__popc(peers));
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int acc = 0, d = 255;
-            for (; d >= 0; --d) {
-                if (acc + (int)hist[d] >= remaining) break;
-                acc += (int)hist[d];
+        if (threadIdx.x < 32) {
+            // digit d with  count(digits > d) < remaining <= count(digits >= d):  lane l owns digits 255-8l .. 248-8l
+            // (descending), a warp scan gives the count above each lane's block, the owning lane walks its 8 digits
+            const int lane = threadIdx.x, top = 255 - 8 * lane;
+            int mine = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mine += (int)hist[top - i];
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-            sh[0] = (unsigned)d;
-            sh[1] = (unsigned)(remaining - acc);
+            int above = incl - mine;
+            if (above < remaining && remaining <= incl) {   // exactly one lane (counts are cumulative and total >= remaining)
+                int d = top;
+                for (;; --d) {
+                    const int h = (int)hist[d];
+                    if (above + h >= remaining) break;
+                    above += h;
+                }
+                sh[0] = (unsigned)d;
+                sh[1] = (unsigned)(remaining - above);
+            }
         }
         __syncthreads();
         prefix |= sh[0] << shift;

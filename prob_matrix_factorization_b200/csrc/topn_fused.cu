@@ -8,7 +8,7 @@
 //   refine    per row: t = n-th largest approximate score so far.  The n-th largest over ALL items can only be larger,
 //             so an item scoring below t - 2*margin can never be needed (margin bounds the bf16 error, see topn.cu);
 //             the list is compacted to the entries above that threshold
-//   level l   the next item range (g times what has been covered, g ~ 1024/n) is scored against the thresholds;
+//   level l   the next item range (g times what has been covered, g ~ 256/n) is scored against the thresholds;
 //             expected survivors per row ~ n*g, far below the list capacity
 //   finish    after the last level the list holds every item with S~ >= t - 2*margin >= (true n-th S~) - 2*margin, i.e.
 //             exactly the candidate set the unfused path proves sufficient: exact fp32 re-score, sort, write the top n
@@ -20,8 +20,11 @@
 //   warp 1        one thread issues tcgen05.mma 128x128x16 (bf16 -> fp32 in TMEM): each item tile is multiplied with
 //                 BOTH user tiles, so every byte of B fetched from L2 feeds 256 rows (L2 read rate 32 B/clk/SM, under
 //                 the ~42 B/clk/SM the L2 sustains chip-wide); two accumulator stages x two row blocks = 512 TMEM columns
-//   warps 2..9    epilogue: warp w drains TMEM lanes 32*(w%4).. of row block (w-2)/4 with tcgen05.ld.x32, takes the
-//                 running maximum of 32 scores and only on a hit walks them to append (item, score) to the row's list
+//   warps 2..17   epilogue, two sets of 8 warps; set s drains accumulator stage s (every other item tile): a warp reads
+//                 TMEM lanes 32*(w%4).. of one row block with tcgen05.ld.x32 (thread = user row), reduces its 32 scores to
+//                 maxima of 4 and of 32 and votes; only groups of 4 in which some lane beats its row's threshold are
+//                 walked, with predicated stores into a shared-memory staging area that the warp flushes to the rows'
+//                 global lists with one list-space reservation per row
 #include "topn.cuh"
 
 namespace pmf {
@@ -29,11 +32,15 @@ namespace pmf {
 constexpr int kFuseCap = 4096;                 // list capacity per row
 constexpr int kLevel0Tiles = kFuseCap / 2 / kTile;   // 16 tiles = 2048 items scored densely
 constexpr int kFuseRows = 2 * kTile;           // user rows per CTA (two UMMA M = 128 row blocks)
-constexpr int kFuseThreads = 320;
+constexpr int kEpiWarps = 16;                  // warps 2..17: two sets of 8, set s drains accumulator stage s
+constexpr int kFuseThreads = 64 + 32 * kEpiWarps;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kStage = 12;                     // survivors staged per epilogue thread before list space is reserved
+constexpr size_t kExtraBytes = (size_t)kEpiThreads * kStage * 8;
 constexpr int kFuseMaxN = 256;                 // level 0 must hold several times n items
 constexpr int kMaxStages = 4;
 constexpr int kFallbackCtas = 148;
-constexpr size_t kFuseSmemBudget = 200 * 1024;
+constexpr size_t kFuseSmemBudget = 220 * 1024;
 
 struct FilterArgs {
     const __nv_bfloat16 *A_pack, *B_pack;
@@ -48,10 +55,41 @@ struct FilterArgs {
     int32_t* cand_cnt;
 };
 
+// Survivors are staged in shared memory, kStage per epilogue thread ([slot][thread]: the lanes of a warp hit distinct
+// banks), and moved to the rows' global lists by the whole warp at once: every lane reserves space in its row's list with
+// ONE returning atomic (all lanes' atomics in flight together) and copies its own entries.  s_*: this thread's staging
+// column; g_*: this thread's row.
+__device__ __noinline__ void stage_flush_all(const int* s_ix, const float* s_sc, int count, int32_t* g_cnt, int32_t* g_ix, float* g_sc) {
+    if (count > 0) {
+        const int base = atomicAdd(g_cnt, count);   // other CTAs (other item ranges) append to the same row
+        for (int i = 0; i < count; ++i) {
+            const int slot = base + i;
+            if (slot < kFuseCap) { g_ix[slot] = s_ix[i * kEpiThreads]; g_sc[slot] = s_sc[i * kEpiThreads]; }
+        }
+    }
+}
+
+// Four scores of one thread against its row's threshold: straight-line, predicated, no register indexing.
+template <bool CHECK>
+__device__ __forceinline__ void push_group(const uint32_t (&r)[32], int i, float thr, int item0, int limit, int* s_ix, float* s_sc,
+                                           int& count) {
+#pragma unroll
+    for (int j = 4 * i; j < 4 * i + 4; ++j) {
+        const float v = __uint_as_float(r[j]);
+        bool p = v >= thr;
+        if (CHECK) p = p && j < limit;       // the last item tile is padded with zero rows
+        if (p) {
+            s_ix[count * kEpiThreads] = item0 + j;
+            s_sc[count * kEpiThreads] = v;
+            ++count;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kFuseThreads, 1) topn_filter_kernel(const FilterArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];   // A0 | A1 | B[stages]
-    __shared__ __align__(8) uint64_t bar_a_full, bar_a_empty, bar_b_full[kMaxStages], bar_b_empty[kMaxStages], bar_acc_full[2],
-        bar_acc_empty[2];
+    extern __shared__ __align__(128) uint8_t smem[];   // A0 | A1 | B[stages] | staging indices | staging scores
+    __shared__ __align__(8) uint64_t bar_a_full, bar_a_empty, bar_b_full[kMaxStages], bar_b_empty[kMaxStages], bar_acc_full[4],
+        bar_acc_empty[4];   // accumulator slot = stage * 2 + row block
     __shared__ uint32_t tmem_base_slot;
     const uint32_t tile_bytes = (uint32_t)kTile * a.kp16 * 2;
     uint8_t* sA = smem;
@@ -62,7 +100,7 @@ __global__ void __launch_bounds__(kFuseThreads, 1) topn_filter_kernel(const Filt
         mbar_init(&bar_a_full, 1);
         mbar_init(&bar_a_empty, 1);
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(&bar_b_full[i], 1); mbar_init(&bar_b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 8); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // all 512 TMEM columns: [stage][row block][128]
@@ -82,11 +120,11 @@ __global__ void __launch_bounds__(kFuseThreads, 1) topn_filter_kernel(const Filt
                 const int rp = unit / a.units_per_rowpair, chunk = unit % a.units_per_rowpair;
                 const int t0 = a.tile_begin + chunk * a.tiles_per_unit;
                 const int t1 = min(t0 + a.tiles_per_unit, a.tile_end);
-                mbar_wait(&bar_a_empty, (ucount & 1u) ^ 1u);   // the previous unit's MMAs no longer read A
+                mbar_wait_sleepy(&bar_a_empty, (ucount & 1u) ^ 1u);   // the previous unit's MMAs no longer read A
                 mbar_expect_tx(&bar_a_full, 2 * tile_bytes);
                 bulk_g2s(sA, reinterpret_cast<const uint8_t*>(a.A_pack) + (size_t)rp * 2 * tile_bytes, 2 * tile_bytes, &bar_a_full);
                 for (int t = t0; t < t1; ++t) {
-                    mbar_wait(&bar_b_empty[bs], bphase ^ 1u);
+                    mbar_wait_sleepy(&bar_b_empty[bs], bphase ^ 1u);
                     mbar_expect_tx(&bar_b_full[bs], tile_bytes);
                     bulk_g2s(sB + (size_t)bs * tile_bytes, reinterpret_cast<const uint8_t*>(a.B_pack) + (size_t)t * tile_bytes,
                              tile_bytes, &bar_b_full[bs]);
@@ -95,54 +133,67 @@ __global__ void __launch_bounds__(kFuseThreads, 1) topn_filter_kernel(const Filt
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16_128x128();
-            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-            const int ksteps = a.kp16 / 16;
-            uint32_t bs = 0, bphase = 0, as = 0, aphase = 0, ucount = 0;
-            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++ucount) {
-                const int chunk = unit % a.units_per_rowpair;
-                const int t0 = a.tile_begin + chunk * a.tiles_per_unit;
-                const int t1 = min(t0 + a.tiles_per_unit, a.tile_end);
-                mbar_wait(&bar_a_full, ucount & 1u);
-                for (int t = t0; t < t1; ++t) {
-                    mbar_wait(&bar_acc_empty[as], aphase ^ 1u);   // epilogue has drained this accumulator stage
-                    mbar_wait(&bar_b_full[bs], bphase);
+        // The whole warp walks the loops (uniform control flow keeps the descriptor arithmetic on the uniform datapath);
+        // one elected lane issues.  Descriptor low word = address/16 | LBO/16 << 16, high word = SBO/16 | version.
+        const uint32_t idesc = umma_idesc_bf16_128x128();
+        const uint32_t tile16 = tile_bytes >> 4;
+        const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (128u << 16);
+        const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (128u << 16);
+        const uint64_t desc_hi = (uint64_t)(8u | (1u << 14)) << 32;
+        const int ksteps = a.kp16 / 16;
+        uint32_t bs = 0, bphase = 0, as = 0, aphase = 0, ucount = 0;
+        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++ucount) {
+            const int chunk = unit % a.units_per_rowpair;
+            const int t0 = a.tile_begin + chunk * a.tiles_per_unit;
+            const int t1 = min(t0 + a.tiles_per_unit, a.tile_end);
+            mbar_wait_sleepy(&bar_a_full, ucount & 1u);
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait_sleepy(&bar_b_full[bs], bphase);
+                const uint32_t b_lo = b_lo0 + bs * tile16;
+#pragma unroll
+                for (int rb = 0; rb < 2; ++rb) {
+                    const uint32_t slot = as * 2u + (uint32_t)rb;
+                    mbar_wait_sleepy(&bar_acc_empty[slot], aphase ^ 1u);   // the epilogue has drained this accumulator
                     tc_fence_after();
-                    const uint32_t b_tile = b_base + bs * tile_bytes;
-#pragma unroll 1
-                    for (int rb = 0; rb < 2; ++rb) {
-                        const uint32_t d = tmem + as * 256u + (uint32_t)rb * 128u;
-                        const uint32_t a_tile = a_base + (uint32_t)rb * tile_bytes;
-                        for (int k = 0; k < ksteps; ++k)   // one MMA consumes K = 16 = two 8-wide k-chunks (LBO = 2048 B apart)
-                            umma_bf16(d, umma_desc(a_tile + (uint32_t)k * 4096u, 2048u, 128u),
-                                      umma_desc(b_tile + (uint32_t)k * 4096u, 2048u, 128u), idesc, k > 0);
+                    if (elect_one()) {
+                        const uint32_t d = tmem + slot * 128u;
+                        const uint32_t a_lo = a_lo0 + (uint32_t)rb * tile16;
+                        for (int k = 0; k < ksteps; ++k)   // one MMA consumes K = 16 = two 8-wide k-chunks = 4096 B of each tile
+                            umma_bf16(d, desc_hi | (a_lo + (uint32_t)k * 256u), desc_hi | (b_lo + (uint32_t)k * 256u), idesc, k > 0);
+                        umma_commit(&bar_acc_full[slot]);                  // this row block's scores are complete -> epilogue
+                        if (rb == 1) umma_commit(&bar_b_empty[bs]);        // item tile consumed -> producer may refill the slot
                     }
-                    umma_commit(&bar_b_empty[bs]);     // item tile consumed -> producer may refill the slot
-                    umma_commit(&bar_acc_full[as]);    // both accumulators of this stage complete -> epilogue
-                    if (++bs == (uint32_t)stages) { bs = 0; bphase ^= 1u; }
-                    if (++as == 2u) { as = 0; aphase ^= 1u; }
+                    __syncwarp();
                 }
-                umma_commit(&bar_a_empty);             // every MMA of the unit done -> A tiles may be replaced
+                if (++bs == (uint32_t)stages) { bs = 0; bphase ^= 1u; }
+                if (++as == 2u) { as = 0; aphase ^= 1u; }
             }
+            if (elect_one()) umma_commit(&bar_a_empty);                    // every MMA of the unit done -> A tiles may be replaced
+            __syncwarp();
         }
     } else {
-        const int rb = (warp - 2) >> 2, q = warp & 3;   // a warp may only touch TMEM lanes 32*(warp%4) .. +31
-        const int cap = kFuseCap;
-        uint32_t as = 0, aphase = 0;
+        const int ew = warp - 2;                        // 0..15
+        const uint32_t set = (uint32_t)ew >> 3;         // the accumulator stage this warp drains (every other item tile)
+        const int rb = (ew & 7) >> 2, q = warp & 3;     // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        int* s_ix = reinterpret_cast<int*>(sB + (size_t)stages * tile_bytes) + (threadIdx.x - 64);   // [kStage][kEpiThreads]
+        float* s_sc = reinterpret_cast<float*>(sB + (size_t)stages * tile_bytes) + kEpiThreads * kStage + (threadIdx.x - 64);
+        int count = 0;                                  // entries staged by this thread
+        uint32_t aphase = 0, gt = 0;                    // gt: item tiles this CTA has gone through (the MMA warp's sequence)
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
             const int rp = unit / a.units_per_rowpair, chunk = unit % a.units_per_rowpair;
             const int t0 = a.tile_begin + chunk * a.tiles_per_unit;
             const int t1 = min(t0 + a.tiles_per_unit, a.tile_end);
-            const int64_t row = (int64_t)rp * kFuseRows + rb * kTile + q * 32 + lane;
-            const float thr = a.thr[row];
-            int32_t* __restrict__ r_idx = a.cand_idx + (size_t)row * cap;
-            float* __restrict__ r_sc = a.cand_score + (size_t)row * cap;
-            for (int t = t0; t < t1; ++t) {
-                mbar_wait(&bar_acc_full[as], aphase);
+            const int64_t row0 = (int64_t)rp * kFuseRows + rb * kTile + q * 32;
+            const float thr = a.thr[row0 + lane];
+            int32_t* g_cnt = a.cand_cnt + row0 + lane;
+            int32_t* g_ix = a.cand_idx + (size_t)(row0 + lane) * kFuseCap;
+            float* g_sc = a.cand_score + (size_t)(row0 + lane) * kFuseCap;
+            for (int t = t0; t < t1; ++t, ++gt) {
+                if ((gt & 1u) != set) continue;
+                mbar_wait_sleepy(&bar_acc_full[set * 2u + (uint32_t)rb], aphase);
                 __syncwarp();
                 tc_fence_after();
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + as * 256u + (uint32_t)rb * 128u;
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + set * 256u + (uint32_t)rb * 128u;
 #pragma unroll 1
                 for (int c0 = 0; c0 < kTile; c0 += 32) {
                     uint32_t r[32];
@@ -153,32 +204,45 @@ __global__ void __launch_bounds__(kFuseThreads, 1) topn_filter_kernel(const Filt
                         if (thr < INFINITY) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
-                                *reinterpret_cast<uint4*>(r_sc + slot0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-                                *reinterpret_cast<int4*>(r_idx + slot0 + j) = make_int4(item0 + j, item0 + j + 1, item0 + j + 2, item0 + j + 3);
+                                *reinterpret_cast<uint4*>(g_sc + slot0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                                *reinterpret_cast<int4*>(g_ix + slot0 + j) = make_int4(item0 + j, item0 + j + 1, item0 + j + 2, item0 + j + 3);
                             }
                         }
-                    } else {
-                        float mx = __uint_as_float(r[0]);
+                        continue;
+                    }
+                    // maxima of groups of 4, then of all 32: ~25 instructions when no lane of the warp has a hit.  Otherwise
+                    // only the groups in which some lane has a hit are walked, with predicated stores into the staging area.
+                    float g[8];
 #pragma unroll
-                        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-                        if (mx >= thr) {
+                    for (int i = 0; i < 8; ++i)
+                        g[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
+                                     fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+                    const float mx = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
+                    if (__any_sync(0xffffffffu, mx >= thr)) {
+                        const int limit = a.n_items - item0;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float v = __uint_as_float(r[j]);
-                                if (v >= thr && item0 + j < a.n_items) {
-                                    const int slot = atomicAdd(a.cand_cnt + row, 1);   // other CTAs append to the same row
-                                    if (slot < cap) { r_idx[slot] = item0 + j; r_sc[slot] = v; }
+                        for (int i = 0; i < 8; ++i) {
+                            if (__any_sync(0xffffffffu, g[i] >= thr)) {
+                                if (__any_sync(0xffffffffu, count > kStage - 4)) {   // a group adds at most 4 entries
+                                    stage_flush_all(s_ix, s_sc, count, g_cnt, g_ix, g_sc);
+                                    count = 0;
                                 }
+                                if (limit >= 32) push_group<false>(r, i, thr, item0, limit, s_ix, s_sc, count);
+                                else push_group<true>(r, i, thr, item0, limit, s_ix, s_sc, count);
                             }
                         }
-                        __syncwarp();
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_acc_empty[as]);
-                if (++as == 2u) { as = 0; aphase ^= 1u; }
+                if (lane == 0) mbar_arrive(&bar_acc_empty[set * 2u + (uint32_t)rb]);
+                aphase ^= 1u;
             }
+            if (__any_sync(0xffffffffu, count > 0)) {   // the next unit works on other rows
+                stage_flush_all(s_ix, s_sc, count, g_cnt, g_ix, g_sc);
+                count = 0;
+            }
+            __syncwarp();
         }
     }
     __syncwarp();
@@ -303,7 +367,7 @@ static int64_t pad_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 static int fused_stages(int kp16) {
     const size_t tile = (size_t)kTile * kp16 * 2;
-    int s = (int)(kFuseSmemBudget / tile) - 2;
+    int s = (int)((kFuseSmemBudget - kExtraBytes) / tile) - 2;
     return s > kMaxStages ? kMaxStages : s;
 }
 
@@ -391,7 +455,7 @@ int topn_fused_run(const TopnProblem& p, void* workspace, int64_t workspace_byte
     PMF_LAUNCH_CHECK();
 
     const int stages = fused_stages(kp16);
-    const size_t smem = (size_t)(2 + stages) * kTile * kp16 * 2;
+    const size_t smem = (size_t)(2 + stages) * kTile * kp16 * 2 + kExtraBytes;
     PMF_CUDA(cudaFuncSetAttribute(topn_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t refine_smem = (size_t)kFuseCap * 8 + (size_t)kCandCap * 8 + (size_t)p.K * 4;
     PMF_CUDA(cudaFuncSetAttribute(topn_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)refine_smem));
@@ -408,7 +472,7 @@ int topn_fused_run(const TopnProblem& p, void* workspace, int64_t workspace_byte
 
     PMF_TRY(launch_filter(fa, 0, level0_tiles, 1, smem, s));
     int covered = level0_tiles;
-    const int growth = 1024 / p.n < 2 ? 2 : 1024 / p.n;   // a level adds ~ n * growth entries per row
+    const int growth = 256 / p.n < 2 ? 2 : 256 / p.n;     // a level adds ~ n * growth entries per row
     while (covered < tiles) {
         ra.final_level = 0;
         topn_refine_kernel<<<(unsigned)p.batch_rows, kSelThreads, refine_smem, s>>>(ra);
