@@ -183,7 +183,6 @@ __device__ void select_row(const SelArgs& a, int64_t row, float* __restrict__ s,
     extern __shared__ float s_user[];   // [K]
     const int M = a.n_items, n = a.n;
     const float* urow = a.F_user + (size_t)(a.rows ? a.rows[row] : row) * a.ld;
-    float un2 = 0.f;
     for (int k = threadIdx.x; k < a.K; k += blockDim.x) s_user[k] = urow[k];
     __syncthreads();
     if (score_first) {
@@ -199,10 +198,7 @@ __device__ void select_row(const SelArgs& a, int64_t row, float* __restrict__ s,
         __syncthreads();
         if (approx) {
             // S~ >= (n-th largest S~) - 2*margin contains the exact top n; margin = 2^-7 |u| max|v| bounds the bf16 error
-            if (threadIdx.x == 0) {
-                for (int k = 0; k < a.K; ++k) un2 = fmaf(s_user[k], s_user[k], un2);
-                sh[2] = __float_as_uint(sqrtf(un2));
-            }
+            row_norm_warp0(s_user, a.K, &sh[2]);
             __syncthreads();
             const float margin = 0.0078125f * __uint_as_float(sh[2]) * sqrtf(__uint_as_float(*a.item_maxnorm2_bits));
             const unsigned kn = key_n;

@@ -12,10 +12,46 @@ constexpr int kTile = 128;          // UMMA M = N = 128
 constexpr int kCandCap = 2048;      // candidates kept per row in shared memory by the selection kernels
 constexpr int kSelThreads = 256;
 
+// The oracle's float32 chain  s = s + u[k]*v[k], k = 0..K-1 (no FMA contraction).  The chain is sequential, so the item row
+// is fetched 32 floats at a time (eight 128-bit loads in flight) instead of one dependent load per step.
 __device__ __forceinline__ float exact_dot(const float* __restrict__ u, const float* __restrict__ v, int K) {
     float s = 0.f;
-    for (int k = 0; k < K; ++k) s = __fadd_rn(s, __fmul_rn(u[k], v[k]));   // no FMA contraction: matches the oracle
+    int k = 0;
+    if ((reinterpret_cast<uintptr_t>(v) & 15u) == 0) {
+        for (; k + 32 <= K; k += 32) {
+            float4 x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = __ldg(reinterpret_cast<const float4*>(v + k) + i);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                s = __fadd_rn(s, __fmul_rn(u[k + 4 * i], x[i].x));
+                s = __fadd_rn(s, __fmul_rn(u[k + 4 * i + 1], x[i].y));
+                s = __fadd_rn(s, __fmul_rn(u[k + 4 * i + 2], x[i].z));
+                s = __fadd_rn(s, __fmul_rn(u[k + 4 * i + 3], x[i].w));
+            }
+        }
+        for (; k + 4 <= K; k += 4) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(v + k));
+            s = __fadd_rn(s, __fmul_rn(u[k], x.x));
+            s = __fadd_rn(s, __fmul_rn(u[k + 1], x.y));
+            s = __fadd_rn(s, __fmul_rn(u[k + 2], x.z));
+            s = __fadd_rn(s, __fmul_rn(u[k + 3], x.w));
+        }
+    }
+    for (; k < K; ++k) s = __fadd_rn(s, __fmul_rn(u[k], v[k]));
     return s;
+}
+
+// |u|^2 of the row staged in shared memory, by warp 0; the result is published through sh_out after the caller's
+// next __syncthreads().
+__device__ __forceinline__ void row_norm_warp0(const float* s_user, int K, unsigned* sh_out) {
+    if (threadIdx.x < 32) {
+        float un2 = 0.f;
+        for (int k = threadIdx.x; k < K; k += 32) un2 = fmaf(s_user[k], s_user[k], un2);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) un2 += __shfl_xor_sync(0xffffffffu, un2, o);
+        if (threadIdx.x == 0) *sh_out = __float_as_uint(sqrtf(un2));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -47,7 +47,7 @@ struct FilterArgs {
     int32_t kp16, stages;
     int32_t n_rowpairs;                  // 256-row blocks of the batch
     int32_t tile_begin, tile_end;        // item tiles of this level
-    int32_t tiles_per_unit, units_per_rowpair;
+    int32_t steps_per_cta;               // the (row block, item tile) steps of the level are dealt out in contiguous runs
     int32_t n_items, dense;
     const float* thr;                    // [rows padded to 256]; +inf for padding rows and rows already overflowed
     int32_t* cand_idx;
@@ -86,6 +86,30 @@ __device__ __forceinline__ void push_group(const uint32_t (&r)[32], int i, float
     }
 }
 
+// Work of a level = n_rowpairs x tiles steps, linearised row block major; CTA b owns steps [b*L, (b+1)*L).  A work unit is
+// the part of that run inside one row block (the A tiles change between units).  Every warp role walks the same units.
+struct UnitWalk {
+    int64_t lin, end;
+    int tiles, tile_begin;
+    __device__ UnitWalk(const FilterArgs& a) {
+        tiles = a.tile_end - a.tile_begin;
+        tile_begin = a.tile_begin;
+        const int64_t total = (int64_t)a.n_rowpairs * tiles;
+        lin = (int64_t)blockIdx.x * a.steps_per_cta;
+        end = lin + a.steps_per_cta < total ? lin + a.steps_per_cta : total;
+    }
+    __device__ bool next(int& rp, int& t0, int& t1) {
+        if (lin >= end) return false;
+        rp = (int)(lin / tiles);
+        const int off = (int)(lin - (int64_t)rp * tiles);
+        const int64_t run = end - lin < tiles - off ? end - lin : tiles - off;
+        t0 = tile_begin + off;
+        t1 = t0 + (int)run;
+        lin += run;
+        return true;
+    }
+};
+
 __global__ void __launch_bounds__(kFuseThreads, 1) topn_filter_kernel(const FilterArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];   // A0 | A1 | B[stages] | staging indices | staging scores
     __shared__ __align__(8) uint64_t bar_a_full, bar_a_empty, bar_b_full[kMaxStages], bar_b_empty[kMaxStages], bar_acc_full[4],
@@ -111,15 +135,12 @@ __global__ void __launch_bounds__(kFuseThreads, 1) topn_filter_kernel(const Filt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
-    const int total_units = a.n_rowpairs * a.units_per_rowpair;
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t bs = 0, bphase = 0, ucount = 0;
-            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++ucount) {
-                const int rp = unit / a.units_per_rowpair, chunk = unit % a.units_per_rowpair;
-                const int t0 = a.tile_begin + chunk * a.tiles_per_unit;
-                const int t1 = min(t0 + a.tiles_per_unit, a.tile_end);
+            UnitWalk walk(a);
+            for (int rp, t0, t1; walk.next(rp, t0, t1); ++ucount) {
                 mbar_wait_sleepy(&bar_a_empty, (ucount & 1u) ^ 1u);   // the previous unit's MMAs no longer read A
                 mbar_expect_tx(&bar_a_full, 2 * tile_bytes);
                 bulk_g2s(sA, reinterpret_cast<const uint8_t*>(a.A_pack) + (size_t)rp * 2 * tile_bytes, 2 * tile_bytes, &bar_a_full);
@@ -142,10 +163,8 @@ __global__ void __launch_bounds__(kFuseThreads, 1) topn_filter_kernel(const Filt
         const uint64_t desc_hi = (uint64_t)(8u | (1u << 14)) << 32;
         const int ksteps = a.kp16 / 16;
         uint32_t bs = 0, bphase = 0, as = 0, aphase = 0, ucount = 0;
-        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++ucount) {
-            const int chunk = unit % a.units_per_rowpair;
-            const int t0 = a.tile_begin + chunk * a.tiles_per_unit;
-            const int t1 = min(t0 + a.tiles_per_unit, a.tile_end);
+        UnitWalk walk(a);
+        for (int rp, t0, t1; walk.next(rp, t0, t1); ++ucount) {
             mbar_wait_sleepy(&bar_a_full, ucount & 1u);
             for (int t = t0; t < t1; ++t) {
                 mbar_wait_sleepy(&bar_b_full[bs], bphase);
@@ -179,10 +198,8 @@ __global__ void __launch_bounds__(kFuseThreads, 1) topn_filter_kernel(const Filt
         float* s_sc = reinterpret_cast<float*>(sB + (size_t)stages * tile_bytes) + kEpiThreads * kStage + (threadIdx.x - 64);
         int count = 0;                                  // entries staged by this thread
         uint32_t aphase = 0, gt = 0;                    // gt: item tiles this CTA has gone through (the MMA warp's sequence)
-        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-            const int rp = unit / a.units_per_rowpair, chunk = unit % a.units_per_rowpair;
-            const int t0 = a.tile_begin + chunk * a.tiles_per_unit;
-            const int t1 = min(t0 + a.tiles_per_unit, a.tile_end);
+        UnitWalk walk(a);
+        for (int rp, t0, t1; walk.next(rp, t0, t1);) {
             const int64_t row0 = (int64_t)rp * kFuseRows + rb * kTile + q * 32;
             const float thr = a.thr[row0 + lane];
             int32_t* g_cnt = a.cand_cnt + row0 + lane;
@@ -203,10 +220,8 @@ __global__ void __launch_bounds__(kFuseThreads, 1) topn_filter_kernel(const Filt
                         const int slot0 = item0 - a.tile_begin * kTile;
                         if (thr < INFINITY) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
+                            for (int j = 0; j < 32; j += 4)   // the item index is the slot: the first refine fills it in
                                 *reinterpret_cast<uint4*>(g_sc + slot0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-                                *reinterpret_cast<int4*>(g_ix + slot0 + j) = make_int4(item0 + j, item0 + j + 1, item0 + j + 2, item0 + j + 3);
-                            }
                         }
                         continue;
                     }
@@ -268,6 +283,7 @@ struct RefineArgs {
     int32_t* cand_cnt;
     float* thr;
     int32_t n, final_level;
+    int32_t dense_input;      // the list is level 0's output: scores only, item index = slot
     const float *F_user, *F_item;
     const int32_t* rows;
     int32_t K, ld;
@@ -277,15 +293,85 @@ struct RefineArgs {
     int32_t* stats;
     int32_t *ovf_list, *ovf_count;
 };
+constexpr int kRefineThreads = 128;
 
-// One CTA per user row.  Dynamic shared memory: list scores | list indices | kept scores | kept indices | user row.
-__global__ void __launch_bounds__(kSelThreads) topn_refine_kernel(const RefineArgs a) {
+// A lower bound of the n-th largest of s[0..c) (c >= n), tight to 2^-16 of the value range.  Thresholds only have to be
+// lower bounds, so instead of four exact radix passes over float keys whose leading bytes all agree, the keys are
+// rebased to the row's minimum and shifted so the top 16 bits carry the spread, then two 8-bit passes pick the bucket
+// of the n-th largest; its lower edge is returned.  hist: 256 counters, sh: 4 words (shared).  All threads must call.
+__device__ __forceinline__ float nth_largest_lower_bound(const float* s, int c, int n, unsigned* hist, unsigned* sh) {
+    unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
+    for (int j = threadIdx.x; j < c; j += blockDim.x) {
+        const unsigned k = order_key(s[j]);
+        kmin = min(kmin, k);
+        kmax = max(kmax, k);
+    }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (threadIdx.x == 0) { sh[2] = 0xFFFFFFFFu; sh[3] = 0u; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { atomicMin(&sh[2], kmin); atomicMax(&sh[3], kmax); }
+    __syncthreads();
+    kmin = sh[2];
+    kmax = sh[3];
+    if (kmax == kmin) return key_to_float(kmin);
+    const int lz = __clz(kmax - kmin);
+    unsigned prefix = 0, mask = 0;
+    int remaining = n;
+    for (int shift = 24; shift >= 16; shift -= 8) {
+        for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+        __syncthreads();
+        for (int j0 = 0; j0 < c; j0 += blockDim.x) {   // uniform trip count: the warp votes below
+            const int j = j0 + threadIdx.x;
+            unsigned digit = 256u;
+            if (j < c) {
+                const unsigned d = (order_key(s[j]) - kmin) << lz;
+                if ((d & mask) == prefix) digit = (d >> shift) & 255u;
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, digit);
+            if (digit != 256u && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned)__popc(peers));
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {   // as in radix_select: lane l owns digits 255-8l .. 248-8l, descending
+            const int lane = threadIdx.x, top = 255 - 8 * lane;
+            int mine = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mine += (int)hist[top - i];
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int above = incl - mine;
+            if (above < remaining && remaining <= incl) {
+                int d = top;
+                for (;; --d) {
+                    const int h = (int)hist[d];
+                    if (above + h >= remaining) break;
+                    above += h;
+                }
+                sh[0] = (unsigned)d;
+                sh[1] = (unsigned)(remaining - above);
+            }
+        }
+        __syncthreads();
+        prefix |= sh[0] << shift;
+        mask |= 255u << shift;
+        remaining = (int)sh[1];
+        __syncthreads();
+    }
+    return key_to_float(kmin + (prefix >> lz));   // every key of the chosen bucket is >= its lower edge
+}
+
+// One CTA per user row.  Dynamic shared memory: user row | list scores | list indices [| kept scores | kept indices].
+__global__ void __launch_bounds__(kRefineThreads) topn_refine_kernel(const RefineArgs a) {
     extern __shared__ __align__(16) uint8_t dyn[];
-    float* l_sc = reinterpret_cast<float*>(dyn);
+    float* s_user = reinterpret_cast<float*>(dyn);                    // [K rounded up to 4]
+    float* l_sc = s_user + ((a.K + 3) & ~3);
     int* l_ix = reinterpret_cast<int*>(l_sc + kFuseCap);
-    float* k_sc = reinterpret_cast<float*>(l_ix + kFuseCap);
+    float* k_sc = reinterpret_cast<float*>(l_ix + kFuseCap);         // kept scores / indices: final level only
     int* k_ix = reinterpret_cast<int*>(k_sc + kCandCap);
-    float* s_user = reinterpret_cast<float*>(k_ix + kCandCap);
     __shared__ unsigned hist[256];
     __shared__ unsigned sh[4];
     __shared__ int s_count;
@@ -300,23 +386,18 @@ __global__ void __launch_bounds__(kSelThreads) topn_refine_kernel(const RefineAr
     if (!bad) {
         const float* urow = a.F_user + (size_t)(a.rows ? a.rows[row] : row) * a.ld;
         for (int k = threadIdx.x; k < a.K; k += blockDim.x) s_user[k] = urow[k];
-        for (int t = threadIdx.x; t < c; t += blockDim.x) { l_sc[t] = g_sc[t]; l_ix[t] = g_ix[t]; }
+        for (int t = threadIdx.x; t < c; t += blockDim.x) { l_sc[t] = g_sc[t]; l_ix[t] = a.dense_input ? t : g_ix[t]; }
         if (threadIdx.x == 0) s_count = 0;
         __syncthreads();
         float thr_new = -INFINITY;
         if (c >= n) {
-            unsigned key_n;
-            int need_eq;
-            radix_select(l_sc, c, n, hist, sh, &key_n, &need_eq);
-            if (threadIdx.x == 0) {
-                float un2 = 0.f;
-                for (int k = 0; k < a.K; ++k) un2 = fmaf(s_user[k], s_user[k], un2);
-                sh[2] = __float_as_uint(sqrtf(un2));
-            }
+            const float nth = nth_largest_lower_bound(l_sc, c, n, hist, sh);
+            __syncthreads();
+            row_norm_warp0(s_user, a.K, &sh[2]);
             __syncthreads();
             // margin = 2^-7 |u| max|v| bounds |S~ - S| (bf16 operands, Cauchy-Schwarz); see topn.cu::select_row
             const float margin = 0.0078125f * __uint_as_float(sh[2]) * sqrtf(__uint_as_float(*a.item_maxnorm2_bits));
-            thr_new = key_to_float(key_n) - 2.f * margin - 1e-30f;
+            thr_new = nth - 2.f * margin - 1e-30f;
         }
         if (!a.final_level) {
             for (int t = threadIdx.x; t < c; t += blockDim.x) {
@@ -408,22 +489,10 @@ static int launch_filter(FilterArgs fa, int tile_begin, int tile_end, int dense,
     fa.tile_begin = tile_begin;
     fa.tile_end = tile_end;
     fa.dense = dense;
-    const int tiles = tile_end - tile_begin;
-    // work unit = one 256-row block x tiles_per_unit item tiles; >= 24 tiles per unit amortise the 2-tile A load, and
-    // the unit count is kept near a multiple of the SM count so the static round-robin ends evenly
-    int upr = 1;
-    if ((int64_t)fa.n_rowpairs * tiles > (int64_t)kNumSMs * 24) {
-        const int64_t units = pad_up(cdiv((int64_t)fa.n_rowpairs * tiles, 32), kNumSMs);
-        upr = (int)cdiv(units, fa.n_rowpairs);
-    } else {
-        upr = (int)cdiv(kNumSMs, fa.n_rowpairs);
-    }
-    if (upr > tiles) upr = tiles;
-    fa.tiles_per_unit = (int)cdiv(tiles, upr);
-    fa.units_per_rowpair = (int)cdiv(tiles, fa.tiles_per_unit);
-    const int64_t total = (int64_t)fa.n_rowpairs * fa.units_per_rowpair;
-    const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);
-    topn_filter_kernel<<<grid, kFuseThreads, smem, s>>>(fa);
+    const int64_t total = (int64_t)fa.n_rowpairs * (tile_end - tile_begin);   // (row block, item tile) steps
+    const int64_t per_cta = cdiv(total, kNumSMs);
+    fa.steps_per_cta = (int32_t)per_cta;
+    topn_filter_kernel<<<(unsigned)cdiv(total, per_cta), kFuseThreads, smem, s>>>(fa);
     PMF_LAUNCH_CHECK();
     return PMF_OK;
 }
@@ -457,8 +526,9 @@ int topn_fused_run(const TopnProblem& p, void* workspace, int64_t workspace_byte
     const int stages = fused_stages(kp16);
     const size_t smem = (size_t)(2 + stages) * kTile * kp16 * 2 + kExtraBytes;
     PMF_CUDA(cudaFuncSetAttribute(topn_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const size_t refine_smem = (size_t)kFuseCap * 8 + (size_t)kCandCap * 8 + (size_t)p.K * 4;
-    PMF_CUDA(cudaFuncSetAttribute(topn_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)refine_smem));
+    const size_t refine_smem = (size_t)kFuseCap * 8 + (size_t)((p.K + 3) & ~3) * 4;      // + kept arrays at the final level
+    const size_t final_smem = refine_smem + (size_t)kCandCap * 8;
+    PMF_CUDA(cudaFuncSetAttribute(topn_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)final_smem));
 
     FilterArgs fa;
     fa.A_pack = A_pack; fa.B_pack = B_pack; fa.kp16 = kp16; fa.stages = stages;
@@ -473,17 +543,19 @@ int topn_fused_run(const TopnProblem& p, void* workspace, int64_t workspace_byte
     PMF_TRY(launch_filter(fa, 0, level0_tiles, 1, smem, s));
     int covered = level0_tiles;
     const int growth = 256 / p.n < 2 ? 2 : 256 / p.n;     // a level adds ~ n * growth entries per row
+    ra.dense_input = 1;
     while (covered < tiles) {
         ra.final_level = 0;
-        topn_refine_kernel<<<(unsigned)p.batch_rows, kSelThreads, refine_smem, s>>>(ra);
+        topn_refine_kernel<<<(unsigned)p.batch_rows, kRefineThreads, refine_smem, s>>>(ra);
         PMF_LAUNCH_CHECK();
+        ra.dense_input = 0;
         const int64_t want = (int64_t)covered * (1 + growth);
         const int next = (int)(want < tiles ? want : tiles);
         PMF_TRY(launch_filter(fa, covered, next, 0, smem, s));
         covered = next;
     }
     ra.final_level = 1;
-    topn_refine_kernel<<<(unsigned)p.batch_rows, kSelThreads, refine_smem, s>>>(ra);
+    topn_refine_kernel<<<(unsigned)p.batch_rows, kRefineThreads, final_smem, s>>>(ra);
     PMF_LAUNCH_CHECK();
 
     SelArgs sa;
