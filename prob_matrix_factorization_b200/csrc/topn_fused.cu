@@ -167,12 +167,12 @@ __global__ void __launch_bounds__(kFuseThreads, 1) topn_filter_kernel(const Filt
         for (int rp, t0, t1; walk.next(rp, t0, t1); ++ucount) {
             mbar_wait_sleepy(&bar_a_full, ucount & 1u);
             for (int t = t0; t < t1; ++t) {
-                mbar_wait_sleepy(&bar_b_full[bs], bphase);
+                mbar_wait(&bar_b_full[bs], bphase);
                 const uint32_t b_lo = b_lo0 + bs * tile16;
 #pragma unroll
                 for (int rb = 0; rb < 2; ++rb) {
                     const uint32_t slot = as * 2u + (uint32_t)rb;
-                    mbar_wait_sleepy(&bar_acc_empty[slot], aphase ^ 1u);   // the epilogue has drained this accumulator
+                    mbar_wait(&bar_acc_empty[slot], aphase ^ 1u);   // the epilogue has drained this accumulator
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t d = tmem + slot * 128u;
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kFuseThreads, 1) topn_filter_kernel(const Filt
             float* g_sc = a.cand_score + (size_t)(row0 + lane) * kFuseCap;
             for (int t = t0; t < t1; ++t, ++gt) {
                 if ((gt & 1u) != set) continue;
-                mbar_wait_sleepy(&bar_acc_full[set * 2u + (uint32_t)rb], aphase);
+                mbar_wait(&bar_acc_full[set * 2u + (uint32_t)rb], aphase);
                 __syncwarp();
                 tc_fence_after();
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + set * 256u + (uint32_t)rb * 128u;
