@@ -117,6 +117,24 @@ int pmf_gamma_pass_p2p(const pmf_csr* csr, int32_t K, int32_t ld,
                        float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior,
                        void* d_workspace, int32_t n_peers, void* const* h_peer_E_self,
                        void* const* h_peer_hyper_mean, void* stream);
+
+/* Extended Poisson MF (poisson_mf_extended_cavi.py:110-164 user side, :169-216 item side):
+ * x_ui ~ Poisson(phi_u psi_i theta_u . beta_i).  One pass over the rows of `csr`:
+ *   shp[r] = a0 + sum_t (x_t / (E_oth[c_t] . E_self[r])) E_oth[c_t] * E_self[r]      (raw dot product, not clamped: :142)
+ *   rte[r] = b0 + sum_t scale_oth[c_t] E_oth[c_t]                                    (:147-148)
+ *   E_self[r] = shp / rte                                                            (:160)
+ *   scale_shp[r] = a0 + sum_t x_t                                                    (:153)
+ *   scale_rte[r] = b0 + sum_t scale_oth[c_t] (E_oth[c_t] . E_self_new[r])            (:163-164, uses the NEW row mean)
+ *   scale_mean[r] = scale_shp / scale_rte                                            (:167)
+ * Rows without observations get the prior (a0, b0) in shp/rte/scale_shp/scale_rte and keep E_self / scale_mean
+ * (:112-118).  d_shp / d_rte may be NULL.  Workspace: pmf_gamma_pass_workspace_bytes.  Single GPU. */
+int pmf_gamma_pass_ext(const pmf_csr* csr, int32_t K, int32_t ld, const float* d_E_oth, const float* d_scale_oth,
+                       float* d_E_self, float* d_shp, float* d_rte, float* d_scale_shp, float* d_scale_rte,
+                       float* d_scale_mean, float a0, float b0, void* d_workspace, void* stream);
+
+/* out[r][:] = scale[r] * F[r][:] for rows x ld floats (folds phi / psi into the factor tables so that the extended
+ * model's predictions phi_u psi_i theta_u . beta_i go through pmf_predict / pmf_eval_stats). */
+int pmf_scale_rows(const float* d_F, const float* d_scale, int64_t rows, int32_t ld, float* d_out, void* stream);
 /* Peer-mappable device memory (CUDA IPC): allocate + export a 64-byte handle / map a peer's handle. */
 int pmf_ipc_alloc(int64_t bytes, void** d_ptr, void* handle64);
 int pmf_ipc_open(const void* handle64, void** d_ptr);

@@ -149,6 +149,89 @@ def poisson_sweeps(u, i, x, K, a0, b0, n_sweeps, seed, n_users=None, n_items=Non
     return st
 
 
+# ----------------------------------------------------------------------------
+# §8f-4: extended Poisson MF (per-user phi_u and per-item psi_i scalars)
+# ----------------------------------------------------------------------------
+def poisson_ext_init(n_users, n_items, K, a0, b0, seed):
+    """poisson_mf_extended_cavi.py:54-76: draws a_theta, a_beta, a_phi, a_psi in this order; every rate = b0."""
+    rng = np.random.default_rng(seed)
+    st = dict(a_theta=a0 + rng.gamma(1.0, 0.1, size=(n_users, K)), a_beta=a0 + rng.gamma(1.0, 0.1, size=(n_items, K)),
+              a_phi=a0 + rng.gamma(1.0, 0.1, size=n_users), a_psi=a0 + rng.gamma(1.0, 0.1, size=n_items),
+              b_theta=b0 * np.ones((n_users, K)), b_beta=b0 * np.ones((n_items, K)),
+              b_phi=b0 * np.ones(n_users), b_psi=b0 * np.ones(n_items))
+    for f in ("theta", "beta", "phi", "psi"):
+        st["E_" + f] = st["a_" + f] / st["b_" + f]
+    return st
+
+
+def poisson_ext_row_pass(row_ptr, perm, other_ids, x, E_self, s_self, E_oth, s_oth, a0, b0):
+    """One side of an extended sweep (poisson_mf_extended_cavi.py:110-164 users / :169-216 items).
+
+    Row r, observations t in original order, c_t the other side's id:
+      dot_t   = E_oth[c_t] . E_self[r]                       (NOT clamped: the clamped rate_est :137-138 is unused)
+      shp[r]  = a0 + sum_t (x_t / dot_t) * E_oth[c_t] * E_self[r]        (:142-143)
+      rte[r]  = b0 + sum_t s_oth[c_t] * E_oth[c_t]                        (:147-148)
+      E_new   = shp[r] / rte[r]                                           (:160)
+      s_shp[r] = a0 + sum_t x_t                                           (:153)
+      s_rte[r] = b0 + sum_t s_oth[c_t] * (E_oth[c_t] . E_new)             (:163-164, in-row Gauss-Seidel)
+    Empty rows: the shape/rate parameters fall back to their priors but the EXPECTATIONS ARE NOT TOUCHED (:112-118
+    `continue`s before :160/:167), so such a row keeps its initial E for ever.  Rows only read their own E_self and the
+    other side's tables, so the pass is Jacobi across rows.  Returns shp, rte, s_shp, s_rte, E_new, sE_new.
+    """
+    R, K = E_self.shape
+    shp, rte = np.empty((R, K)), np.empty((R, K))
+    s_shp, s_rte = np.empty(R), np.empty(R)
+    E_new, sE_new = E_self.copy(), s_self.copy()
+    for r in range(R):
+        obs = perm[row_ptr[r]:row_ptr[r + 1]]
+        if obs.size == 0:
+            shp[r], rte[r], s_shp[r], s_rte[r] = a0, b0, a0, b0
+            continue
+        sub = E_oth[other_ids[obs]]
+        sc = s_oth[other_ids[obs]]
+        own = E_self[r]
+        dot = sub @ own
+        with np.errstate(divide="ignore", invalid="ignore"):
+            alloc = (x[obs][:, None] / dot[:, None]) * sub * own[None, :]
+        shp[r] = a0 + np.sum(alloc, axis=0)
+        rte[r] = b0 + np.sum(sub * sc[:, None], axis=0)
+        new = shp[r] / rte[r]
+        s_shp[r] = a0 + np.sum(x[obs])
+        s_rte[r] = b0 + np.sum(sc * (sub @ new))
+        E_new[r], sE_new[r] = new, s_shp[r] / s_rte[r]
+    return shp, rte, s_shp, s_rte, E_new, sE_new
+
+
+def poisson_ext_sweeps(u, i, x, K, a0, b0, n_sweeps, seed, n_users=None, n_items=None):
+    """T sweeps of the extended model (poisson_mf_extended_cavi.py:89-216), no validation."""
+    u = np.asarray(u, dtype=np.int64)
+    i = np.asarray(i, dtype=np.int64)
+    x = np.asarray(x, dtype=np.float64)
+    if n_users is None:
+        n_users, n_items = infer_dimensions(u, i)
+    st = poisson_ext_init(n_users, n_items, K, a0, b0, seed)
+    rp_u, pm_u = group_observations(u, n_users)
+    rp_i, pm_i = group_observations(i, n_items)
+    for _ in range(n_sweeps):
+        st["a_theta"], st["b_theta"], st["a_phi"], st["b_phi"], st["E_theta"], st["E_phi"] = poisson_ext_row_pass(
+            rp_u, pm_u, i, x, st["E_theta"], st["E_phi"], st["E_beta"], st["E_psi"], a0, b0)
+        st["a_beta"], st["b_beta"], st["a_psi"], st["b_psi"], st["E_beta"], st["E_psi"] = poisson_ext_row_pass(
+            rp_i, pm_i, u, x, st["E_beta"], st["E_psi"], st["E_theta"], st["E_phi"], a0, b0)
+    st["n_users"], st["n_items"] = n_users, n_items
+    return st
+
+
+def poisson_ext_predict(user_ids, item_ids, st):
+    """phi_u * psi_i * (theta_u . beta_i), 0 for unseen ids (poisson_mf_extended_cavi.py:239-258)."""
+    user_ids = np.asarray(user_ids, dtype=np.int64)
+    item_ids = np.asarray(item_ids, dtype=np.int64)
+    out = np.zeros(len(user_ids))
+    ok = (user_ids < st["E_theta"].shape[0]) & (item_ids < st["E_beta"].shape[0])
+    uu, ii = user_ids[ok], item_ids[ok]
+    out[ok] = st["E_phi"][uu] * st["E_psi"][ii] * np.sum(st["E_theta"][uu] * st["E_beta"][ii], axis=1)
+    return out
+
+
 def hpf_sweeps(u, i, x, K, cfg, n_sweeps, seed, n_users=None, n_items=None):
     """T full sweeps of observed-only HPF-CAVI (hpf_cavi.py:109-193), no validation.
 

@@ -66,6 +66,8 @@ _PROTOTYPES = {
                                  VP, VP, C.c_float, C.c_float, VP, VP]),
     "pmf_gamma_pass_p2p": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP, VP, VP, C.c_float, C.c_float, VP,
                                      VP, VP, C.c_float, C.c_float, VP, C.c_int32, C.POINTER(VP), C.POINTER(VP), VP]),
+    "pmf_gamma_pass_ext": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP, VP, VP, VP, VP, VP, VP, C.c_float, C.c_float, VP, VP]),
+    "pmf_scale_rows": (C.c_int, [VP, VP, C.c_int64, C.c_int32, VP, VP]),
     "pmf_ipc_alloc": (C.c_int, [C.c_int64, C.POINTER(VP), VP]),
     "pmf_ipc_open": (C.c_int, [VP, C.POINTER(VP)]),
     "pmf_ipc_close": (C.c_int, [VP]),

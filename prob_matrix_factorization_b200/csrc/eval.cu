@@ -145,6 +145,16 @@ static unsigned eval_grid(int64_t n) {
     return (unsigned)(blocks < cap ? blocks : cap);
 }
 
+__global__ void scale_rows_kernel(const float* __restrict__ F, const float* __restrict__ scale, int64_t n4, int ld4,
+                                  float* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n4) return;
+    const float sc = scale[e / ld4];
+    float4 v = reinterpret_cast<const float4*>(F)[e];
+    v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+    reinterpret_cast<float4*>(out)[e] = v;
+}
+
 }  // namespace pmf
 
 using namespace pmf;
@@ -178,6 +188,16 @@ int pmf_eval_stats(const int32_t* d_users, const int32_t* d_items, const float* 
     PMF_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * (4 + 2 * (size_t)n_labels), s));
     if (n == 0) return PMF_OK;
     eval_stats_kernel<<<eval_grid(n), 256, 0, s>>>(a, d_y, n_labels > 0 ? d_label : nullptr, n_labels, drop_invalid, d_out);
+    PMF_LAUNCH_CHECK();
+    return PMF_OK;
+}
+
+int pmf_scale_rows(const float* d_F, const float* d_scale, int64_t rows, int32_t ld, float* d_out, void* stream) {
+    PMF_REQUIRE(rows >= 0 && ld > 0 && ld % 4 == 0, "bad shape");
+    if (rows == 0) return PMF_OK;
+    PMF_REQUIRE(d_F && d_scale && d_out, "NULL argument");
+    const int64_t n4 = rows * (ld / 4);
+    scale_rows_kernel<<<(unsigned)cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>(d_F, d_scale, n4, ld / 4, d_out);
     PMF_LAUNCH_CHECK();
     return PMF_OK;
 }

@@ -17,6 +17,12 @@
 // segment order (deterministic, no atomics).
 //
 // HBM-bound: 4*ld + 8 bytes per observation, 16*ld + 4 per row.
+//
+// MODE (template): 0 plain Poisson MF, 1 HPF (rate prior per row + hyper-rate update in the epilogue), 2 extended
+// Poisson MF (poisson_mf_extended_cavi.py:110-216): per-row scalars phi / psi scale the rate sums, the allocation
+// divides by the UNCLAMPED dot product (the reference's clamped rate_est :137-138 is never used), the scalar's rate
+// uses the row's NEW mean (in-row Gauss-Seidel :160-164), and rows without observations get prior shape/rate but keep
+// their expectations (:112-118 `continue`).
 #include "common.cuh"
 
 namespace pmf {
@@ -38,6 +44,11 @@ struct GammaArgs {
     float* hyper_mean;
     float hyper_shape, hyper_rate_prior;
     float* partial;  // [n_partial][2*ld]: sum (x/rate) E_oth | sum E_oth
+    // MODE 2: scale_oth = the other side's scalar means (psi for the user pass); the row's own scalar goes to scale_shp
+    // (shape), hyper_rate (rate) and hyper_mean (mean); partial_x[n_partial] holds the segments' rating sums
+    const float* scale_oth;
+    float* scale_shp;
+    float* partial_x;
     // fused row exchange (multi-GPU): the other ranks' replicas of E_self / hyper_mean, mapped over NVLink.
     // Every finished row is stored to all replicas by the same kernel that computed it.
     // block -> chunk of the longest-first segment list: chunk = (blockIdx.x * block_stride) % gridDim.x with
@@ -67,10 +78,10 @@ __device__ __forceinline__ unsigned group_mask(int lane) {
 }
 
 // Gamma update for global row R from the row's complete sums.  Executed by the G lanes of a group.
-template <int G, int V, bool HYPER>
+template <int G, int V, int MODE>
 __device__ __forceinline__ void gamma_row_update(const GammaArgs& a, int R, int gl, unsigned gmask,
                                                  const float4 (&self)[V], const float4 (&sa)[V],
-                                                 const float4 (&sb)[V]) {
+                                                 const float4 (&sb)[V], float sx = 0.f, bool empty = false) {
     const float rp = a.rate_prior_vec ? a.rate_prior_vec[R] : a.rate_prior;
     float esum = 0.f;
     const size_t rowoff = (size_t)R * a.ld;
@@ -91,16 +102,31 @@ __device__ __forceinline__ void gamma_row_update(const GammaArgs& a, int R, int 
             if (k0 + 3 >= a.K) { s.w = 0.f; r.w = 1.f; e.w = 0.f; }
             if (a.shp) *reinterpret_cast<float4*>(a.shp + rowoff + k0) = s;
             if (a.rte) *reinterpret_cast<float4*>(a.rte + rowoff + k0) = r;
+            if constexpr (MODE == 2) {
+                // scalar rate: sum_t s_oth[c_t] (E_oth[c_t] . E_new) = E_new . sum_t s_oth[c_t] E_oth[c_t] = E_new . sb
+                esum += (e.x * sb[v].x + e.y * sb[v].y) + (e.z * sb[v].z + e.w * sb[v].w);
+                if (empty) continue;   // no observations: prior shape/rate, expectations untouched (:112-118)
+            }
             *reinterpret_cast<float4*>(a.E_self + rowoff + k0) = e;
             for (int pr = 0; pr < a.n_peers; ++pr)   // P2P stores: 16*G contiguous bytes per group and peer
                 *reinterpret_cast<float4*>(a.peer_E[pr] + rowoff + k0) = e;
             if (a.mc_E)   // one store, replicated to every GPU of the multicast group by the NVSwitch
                 asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
                              ::"l"(a.mc_E + rowoff + k0), "f"(e.x), "f"(e.y), "f"(e.z), "f"(e.w) : "memory");
-            esum += (e.x + e.y) + (e.z + e.w);
+            if constexpr (MODE != 2) esum += (e.x + e.y) + (e.z + e.w);
         }
     }
-    if (HYPER) {
+    if constexpr (MODE == 2) {
+        esum = group_sum<G>(esum, gmask);
+        if (gl == 0) {
+            const float s_shp = a.shape_prior + sx;      // :153  a_phi = a0 + sum_t x_t
+            const float s_rte = a.rate_prior + esum;     // :164  b_phi = b0 + sum_t psi_t (beta_t . theta_new)
+            a.scale_shp[R] = s_shp;
+            a.hyper_rate[R] = s_rte;
+            if (!empty) a.hyper_mean[R] = s_shp / s_rte;
+        }
+    }
+    if constexpr (MODE == 1) {
         esum = group_sum<G>(esum, gmask);
         if (gl == 0) {
             const float hr = a.hyper_rate_prior + esum;   // hpf_cavi.py:158 / :192
@@ -113,7 +139,7 @@ __device__ __forceinline__ void gamma_row_update(const GammaArgs& a, int R, int 
     }
 }
 
-template <int G, int V, int U, bool HYPER>
+template <int G, int V, int U, int MODE>
 __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
     static_assert(G == 4 || G == 8 || G == 16 || G == 32, "group size");
     static_assert(G % U == 0, "U must divide G");
@@ -133,6 +159,7 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
     }
     const int R = a.row_offset + row;
     float4 self[V], sa[V], sb[V];
+    float sx = 0.f;   // MODE 2: sum of the segment's ratings (every lane of the group holds the same value)
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         const int idx = gl + v * G;
@@ -140,6 +167,7 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
         sa[v] = f4_zero();
         sb[v] = f4_zero();
     }
+    const bool empty = end == p;
     // warp-uniform trip count so that full-mask shuffles are legal; short groups idle on predicates
     const int maxlen = __reduce_max_sync(0xffffffffu, end - p);
     // column ids / ratings are fetched one chunk ahead, so the dependent chain per chunk is one memory
@@ -156,11 +184,13 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
 #pragma unroll
         for (int j0 = 0; j0 < G; j0 += U) {
             float4 o[U][V];
+            float so[U];   // MODE 2: the gathered rows' scalars
 #pragma unroll
             for (int jj = 0; jj < U; ++jj) {
                 const int j = j0 + jj;
                 const int c = __shfl_sync(0xffffffffu, c_l, j, G);
                 const float* rowp = a.E_oth + (size_t)c * a.ld;
+                if constexpr (MODE == 2) so[jj] = j < rem ? __ldg(a.scale_oth + c) : 0.f;
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     const int idx = gl + v * G;
@@ -180,6 +210,20 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
                     d = fmaf(self[v].w, o[jj][v].w, d);
                 }
                 d = group_sum<G>(d);
+                if constexpr (MODE == 2) {
+                    // poisson_mf_extended_cavi.py:142 divides by the raw dot product; lanes past the segment end add 0
+                    const float w = j < rem ? x / d : 0.f;
+                    const float ps = so[jj];
+                    sx += x;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        sa[v].x = fmaf(w, o[jj][v].x, sa[v].x);  sb[v].x = fmaf(ps, o[jj][v].x, sb[v].x);
+                        sa[v].y = fmaf(w, o[jj][v].y, sa[v].y);  sb[v].y = fmaf(ps, o[jj][v].y, sb[v].y);
+                        sa[v].z = fmaf(w, o[jj][v].z, sa[v].z);  sb[v].z = fmaf(ps, o[jj][v].z, sb[v].z);
+                        sa[v].w = fmaf(w, o[jj][v].w, sa[v].w);  sb[v].w = fmaf(ps, o[jj][v].w, sb[v].w);
+                    }
+                    continue;
+                }
                 const float w = x / fmaxf(d, 1e-10f);  // poisson_mf_cavi.py:153,157 (x = 0 past the segment end)
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
@@ -193,8 +237,9 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
     }
     if (!has) return;
     if (pidx < 0) {  // the whole row lives in this segment: finish it here
-        gamma_row_update<G, V, HYPER>(a, R, gl, group_mask<G>(lane), self, sa, sb);
+        gamma_row_update<G, V, MODE>(a, R, gl, group_mask<G>(lane), self, sa, sb, sx, empty);
     } else {
+        if constexpr (MODE == 2) if (gl == 0) a.partial_x[pidx] = sx;
         float* dst = a.partial + (size_t)pidx * 2 * a.ld;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
@@ -211,10 +256,10 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
 // partial (independent loads in flight, so a row with hundreds of partials costs a few round trips, not
 // hundreds), park their sums in shared memory, and group 0 folds them in group order and applies the
 // same row update.  Deterministic; no atomics.
-template <int G, int V, bool HYPER>
+template <int G, int V, int MODE>
 __global__ void __launch_bounds__(256) gamma_multi_kernel(const GammaArgs a) {
     constexpr int NG = 256 / G;
-    extern __shared__ float s_part[];   // [NG][2*ld]
+    extern __shared__ float s_part[];   // [NG][2*ld] (+ [NG] rating sums, MODE 2)
     const int lane = threadIdx.x & 31;
     const int gl = threadIdx.x & (G - 1);
     const int grp = threadIdx.x / G;
@@ -222,9 +267,11 @@ __global__ void __launch_bounds__(256) gamma_multi_kernel(const GammaArgs a) {
     const int first = a.multi_first[blockIdx.x], last = a.multi_first[blockIdx.x + 1];
     const int R = a.row_offset + row;
     float4 sa[V], sb[V];
+    float sx = 0.f;
 #pragma unroll
     for (int v = 0; v < V; ++v) { sa[v] = f4_zero(); sb[v] = f4_zero(); }
     for (int q = first + grp; q < last; q += NG) {
+        if constexpr (MODE == 2) sx += a.partial_x[q];
         const float* src = a.partial + (size_t)q * 2 * a.ld;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
@@ -239,6 +286,7 @@ __global__ void __launch_bounds__(256) gamma_multi_kernel(const GammaArgs a) {
     }
     const int used = min(NG, last - first);   // groups that saw at least one partial
     if (grp > 0 && grp < used) {
+        if constexpr (MODE == 2) if (gl == 0) s_part[(size_t)NG * 2 * a.ld + grp] = sx;
         float* dst = s_part + (size_t)grp * 2 * a.ld;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
@@ -258,6 +306,7 @@ __global__ void __launch_bounds__(256) gamma_multi_kernel(const GammaArgs a) {
         self[v] = (idx < a.nvec) ? *reinterpret_cast<const float4*>(a.E_self + (size_t)R * a.ld + idx * 4) : f4_zero();
     }
     for (int g = 1; g < used; ++g) {
+        if constexpr (MODE == 2) sx += s_part[(size_t)NG * 2 * a.ld + g];
         const float* src = s_part + (size_t)g * 2 * a.ld;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
@@ -270,7 +319,7 @@ __global__ void __launch_bounds__(256) gamma_multi_kernel(const GammaArgs a) {
             }
         }
     }
-    gamma_row_update<G, V, HYPER>(a, R, gl, group_mask<G>(lane), self, sa, sb);
+    gamma_row_update<G, V, MODE>(a, R, gl, group_mask<G>(lane), self, sa, sb, sx, false);
 }
 
 static int g_tune_interleave = 0;   // 1 = golden-ratio block interleave of the longest-first order (experiment)
@@ -283,7 +332,7 @@ static uint32_t gcd_u32(uint32_t x, uint32_t y) {
 }
 
 template <int G, int V, int U>
-static int launch_gamma(const GammaArgs& a_in, bool hyper, cudaStream_t s) {
+static int launch_gamma(const GammaArgs& a_in, int mode, cudaStream_t s) {
     GammaArgs a = a_in;
     if (a.n_seg > 0) {
         const unsigned grid = (unsigned)cdiv((int64_t)a.n_seg * G, 256);
@@ -296,18 +345,44 @@ static int launch_gamma(const GammaArgs& a_in, bool hyper, cudaStream_t s) {
             while (gcd_u32(st, grid) != 1) st += 2;
             a.block_stride = st % grid;
         }
-        if (hyper) gamma_pass_kernel<G, V, U, true><<<grid, 256, 0, s>>>(a);
-        else gamma_pass_kernel<G, V, U, false><<<grid, 256, 0, s>>>(a);
+        if (mode == 2) gamma_pass_kernel<G, V, U, 2><<<grid, 256, 0, s>>>(a);
+        else if (mode == 1) gamma_pass_kernel<G, V, U, 1><<<grid, 256, 0, s>>>(a);
+        else gamma_pass_kernel<G, V, U, 0><<<grid, 256, 0, s>>>(a);
         PMF_LAUNCH_CHECK();
     }
     if (a.n_multi > 0) {
         const unsigned grid = (unsigned)a.n_multi;
-        const size_t smem = (size_t)(256 / G) * 2 * a.ld * sizeof(float);   // <= 32 KB for every (G, ld) dispatched
-        if (hyper) gamma_multi_kernel<G, V, true><<<grid, 256, smem, s>>>(a);
-        else gamma_multi_kernel<G, V, false><<<grid, 256, smem, s>>>(a);
+        const size_t smem = (size_t)(256 / G) * (2 * a.ld + 1) * sizeof(float);   // <= 33 KB for every (G, ld) dispatched
+        if (mode == 2) gamma_multi_kernel<G, V, 2><<<grid, 256, smem, s>>>(a);
+        else if (mode == 1) gamma_multi_kernel<G, V, 1><<<grid, 256, smem, s>>>(a);
+        else gamma_multi_kernel<G, V, 0><<<grid, 256, smem, s>>>(a);
         PMF_LAUNCH_CHECK();
     }
     return PMF_OK;
+}
+
+static void fill_csr_args(GammaArgs& a, const CsrView& c, int32_t K, int32_t ld) {
+    a.seg_row = c.seg_row; a.seg_start = c.seg_start; a.seg_partial = c.seg_partial; a.seg_order = c.seg_order;
+    a.row_ptr = c.row_ptr;
+    a.col = c.col; a.val = c.val; a.multi_row = c.multi_row; a.multi_first = c.multi_first;
+    a.n_seg = c.n_seg; a.n_multi = c.n_multi; a.seg_len = c.seg_len; a.row_offset = c.row_offset;
+    a.K = K; a.ld = ld; a.nvec = ld / 4;
+    a.scale_oth = nullptr; a.scale_shp = nullptr; a.partial_x = nullptr;
+}
+
+static int dispatch_gamma(const GammaArgs& a, int mode, cudaStream_t s) {
+    const int nv = a.nvec;
+    if (nv <= 4) return launch_gamma<4, 1, 4>(a, mode, s);
+    if (nv <= 8) return g_tune_unroll == 4 ? launch_gamma<8, 1, 4>(a, mode, s) : launch_gamma<8, 1, 8>(a, mode, s);
+    if (nv <= 16) {
+        if (g_tune_group == 16) return g_tune_unroll == 8 ? launch_gamma<16, 1, 8>(a, mode, s) : launch_gamma<16, 1, 4>(a, mode, s);
+        if (g_tune_unroll == 4) return launch_gamma<8, 2, 4>(a, mode, s);
+        if (g_tune_unroll == 2) return launch_gamma<8, 2, 2>(a, mode, s);
+        return launch_gamma<8, 2, 8>(a, mode, s);   // measured best on C5 (profiles/README.md)
+    }
+    if (nv <= 24) return launch_gamma<8, 3, 2>(a, mode, s);
+    if (nv <= 32) return launch_gamma<8, 4, 2>(a, mode, s);
+    return launch_gamma<16, 4, 2>(a, mode, s);
 }
 
 }  // namespace pmf
@@ -328,7 +403,8 @@ int pmf_tune(const char* key, int value) {
 int64_t pmf_gamma_pass_workspace_bytes(const pmf_csr* csr, int32_t ld) {
     if (!csr || ld <= 0) return -1;
     const CsrView c = csr_view(csr);
-    const int64_t b = (int64_t)c.n_partial * 2 * ld * (int64_t)sizeof(float);
+    // per partial: 2*ld floats of row sums + one rating sum (extended model only)
+    const int64_t b = (int64_t)c.n_partial * (2 * ld + 1) * (int64_t)sizeof(float);
     return b > 0 ? b : 16;
 }
 
@@ -353,11 +429,7 @@ int pmf_gamma_pass_p2p(const pmf_csr* csr, int32_t K, int32_t ld, const float* d
     const CsrView c = csr_view(csr);
     PMF_REQUIRE(c.n_partial == 0 || d_workspace != nullptr, "workspace is NULL but %d partial sums are needed", c.n_partial);
     GammaArgs a;
-    a.seg_row = c.seg_row; a.seg_start = c.seg_start; a.seg_partial = c.seg_partial; a.seg_order = c.seg_order;
-    a.row_ptr = c.row_ptr;
-    a.col = c.col; a.val = c.val; a.multi_row = c.multi_row; a.multi_first = c.multi_first;
-    a.n_seg = c.n_seg; a.n_multi = c.n_multi; a.seg_len = c.seg_len; a.row_offset = c.row_offset;
-    a.K = K; a.ld = ld; a.nvec = ld / 4;
+    fill_csr_args(a, c, K, ld);
     a.E_oth = d_E_oth; a.E_self = d_E_self; a.shp = d_shp; a.rte = d_rte;
     a.shape_prior = shape_prior; a.rate_prior = rate_prior; a.rate_prior_vec = d_rate_prior_vec;
     a.hyper_rate = d_hyper_rate; a.hyper_mean = d_hyper_mean; a.hyper_shape = hyper_shape;
@@ -374,20 +446,28 @@ int pmf_gamma_pass_p2p(const pmf_csr* csr, int32_t K, int32_t ld, const float* d
         a.peer_E[pr] = pr < n_peers ? (float*)h_peer_E_self[pr] : nullptr;
         a.peer_hyper_mean[pr] = (pr < n_peers && h_peer_hyper_mean) ? (float*)h_peer_hyper_mean[pr] : nullptr;
     }
-    const bool hyper = d_hyper_rate != nullptr;
-    cudaStream_t s = (cudaStream_t)stream;
-    const int nv = a.nvec;
-    if (nv <= 4) return launch_gamma<4, 1, 4>(a, hyper, s);
-    if (nv <= 8) return g_tune_unroll == 4 ? launch_gamma<8, 1, 4>(a, hyper, s) : launch_gamma<8, 1, 8>(a, hyper, s);
-    if (nv <= 16) {
-        if (g_tune_group == 16) return g_tune_unroll == 8 ? launch_gamma<16, 1, 8>(a, hyper, s) : launch_gamma<16, 1, 4>(a, hyper, s);
-        if (g_tune_unroll == 4) return launch_gamma<8, 2, 4>(a, hyper, s);
-        if (g_tune_unroll == 2) return launch_gamma<8, 2, 2>(a, hyper, s);
-        return launch_gamma<8, 2, 8>(a, hyper, s);   // measured best on C5 (profiles/README.md)
-    }
-    if (nv <= 24) return launch_gamma<8, 3, 2>(a, hyper, s);
-    if (nv <= 32) return launch_gamma<8, 4, 2>(a, hyper, s);
-    return launch_gamma<16, 4, 2>(a, hyper, s);
+    return dispatch_gamma(a, d_hyper_rate != nullptr ? 1 : 0, (cudaStream_t)stream);
+}
+
+int pmf_gamma_pass_ext(const pmf_csr* csr, int32_t K, int32_t ld, const float* d_E_oth, const float* d_scale_oth,
+                       float* d_E_self, float* d_shp, float* d_rte, float* d_scale_shp, float* d_scale_rte,
+                       float* d_scale_mean, float a0, float b0, void* d_workspace, void* stream) {
+    PMF_REQUIRE(csr != nullptr, "csr is NULL");
+    PMF_REQUIRE(K >= 1 && ld >= K && ld % 8 == 0 && ld <= 256, "need 1 <= K <= ld <= 256 and ld %% 8 == 0 (K=%d ld=%d)", K, ld);
+    PMF_REQUIRE(d_E_oth && d_scale_oth && d_E_self && d_scale_shp && d_scale_rte && d_scale_mean, "NULL table");
+    const CsrView c = csr_view(csr);
+    PMF_REQUIRE(c.n_partial == 0 || d_workspace != nullptr, "workspace is NULL but %d partial sums are needed", c.n_partial);
+    GammaArgs a;
+    fill_csr_args(a, c, K, ld);
+    a.E_oth = d_E_oth; a.E_self = d_E_self; a.shp = d_shp; a.rte = d_rte;
+    a.shape_prior = a0; a.rate_prior = b0; a.rate_prior_vec = nullptr;
+    a.hyper_rate = d_scale_rte; a.hyper_mean = d_scale_mean; a.hyper_shape = 0.f; a.hyper_rate_prior = 0.f;
+    a.partial = (float*)d_workspace;
+    a.partial_x = a.partial ? a.partial + (size_t)c.n_partial * 2 * ld : nullptr;
+    a.scale_oth = d_scale_oth; a.scale_shp = d_scale_shp;
+    a.mc_E = nullptr; a.n_peers = 0;
+    for (int pr = 0; pr < kMaxPeers; ++pr) { a.peer_E[pr] = nullptr; a.peer_hyper_mean[pr] = nullptr; }
+    return dispatch_gamma(a, 2, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -7,6 +7,7 @@ The reference's tuning / compare / train scripts import the models by module pat
     from src.models.poisson_mf_cavi import PoissonMFCAVI, PoissonMFCAVIConfig
     from src.models.hpf_cavi import HPF_CAVI, HPF_CAVI_Config
     from src.models.hpf_pytorch import HPF_PyTorch, HPF_PyTorch_Config
+    from src.models.poisson_mf_extended_cavi import PoissonMFExtendedCAVI, PoissonMFExtendedCAVIConfig   (run_poisson_mf_extended.py:4)
 
 ``install()`` registers this package's modules under those names in ``sys.modules`` so that the scripts
 run unchanged on top of libpmf_b200:
@@ -25,7 +26,8 @@ import runpy
 import sys
 import types
 
-MODEL_MODULES = ("poisson_mf_cavi", "hpf_cavi", "gaussian_mf_cavi", "gaussian_mf_cavi_bias", "hpf_pytorch")
+MODEL_MODULES = ("poisson_mf_cavi", "poisson_mf_extended_cavi", "hpf_cavi", "gaussian_mf_cavi", "gaussian_mf_cavi_bias",
+                 "hpf_pytorch")
 
 
 def _package(name, path=None):

@@ -40,6 +40,8 @@ from src.models.hpf_pytorch import HPF_PyTorch as RefHPFTorch  # noqa: E402
 from src.models.hpf_pytorch import HPF_PyTorch_Config as RefHPFTorchCfg  # noqa: E402
 from src.models.poisson_mf_cavi import PoissonMFCAVI as RefPoisson  # noqa: E402
 from src.models.poisson_mf_cavi import PoissonMFCAVIConfig as RefPoissonCfg  # noqa: E402
+from src.models.poisson_mf_extended_cavi import PoissonMFExtendedCAVI as RefPoissonExt  # noqa: E402
+from src.models.poisson_mf_extended_cavi import PoissonMFExtendedCAVIConfig as RefPoissonExtCfg  # noqa: E402
 
 N_USERS, N_ITEMS, NNZ, SEED = 300, 400, 1500, 777
 
@@ -96,6 +98,24 @@ def golden_poisson():
     n_it, _ = iterations_run(lambda: m2.fit(tr, va))
     out.update(es_tol=2e-3, es_max_iter=40, es_iterations=n_it, es_E_theta=m2.E_theta, es_val_rmse=m2.evaluate_rmse(va))
     save("poisson", **out)
+
+
+def golden_poisson_ext():
+    tr, va, te = frames()
+    K, T = 7, 6
+    names = ("a_theta", "b_theta", "a_beta", "b_beta", "a_phi", "b_phi", "a_psi", "b_psi", "E_theta", "E_beta", "E_phi", "E_psi")
+    cfg = RefPoissonExtCfg(n_factors=K, a0=0.3, b0=1.0, max_iter=T, tol=None, random_state=42, verbose=False)
+    m = RefPoissonExt(cfg).fit(tr)
+    out = base_inputs(tr, va, te)
+    out.update(K=K, T=T, a0=0.3, b0=1.0, seed=42, n_users=m.n_users, n_items=m.n_items,
+               val_pred=m.predict(va["u"].to_numpy(), va["i"].to_numpy()), val_rmse=m.evaluate_rmse(va),
+               test_rmse=m.evaluate_rmse(te), **{k: getattr(m, k) for k in names})
+    cfg2 = RefPoissonExtCfg(n_factors=K, a0=0.3, b0=1.0, max_iter=40, tol=2e-3, random_state=42, verbose=True)
+    m2 = RefPoissonExt(cfg2)
+    n_it, _ = iterations_run(lambda: m2.fit(tr, va))
+    out.update(es_tol=2e-3, es_max_iter=40, es_iterations=n_it, es_E_theta=m2.E_theta, es_E_phi=m2.E_phi,
+               es_val_rmse=m2.evaluate_rmse(va))
+    save("poisson_ext", **out)
 
 
 def golden_hpf():
@@ -213,7 +233,12 @@ def golden_hpf_torch():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:            # python make_golden.py poisson_ext  -> only that fixture (versions.json untouched)
+        for name in sys.argv[1:]:
+            globals()["golden_" + name]()
+        sys.exit(0)
     golden_poisson()
+    golden_poisson_ext()
     golden_hpf()
     golden_gauss()
     golden_hpf_torch()

@@ -37,6 +37,20 @@ def test_poisson_sweeps(golden):
     assert abs(lpl - g["test_lpl"]) < 1e-9 * abs(g["test_lpl"])
 
 
+def test_poisson_ext_sweeps(golden):
+    """Extended Poisson MF incl. its quirk: rows without observations keep their initial expectations."""
+    g = golden("poisson_ext")
+    st = O.poisson_ext_sweeps(g["u"], g["i"], g["x"], g["K"], g["a0"], g["b0"], g["T"], g["seed"])
+    assert (st["n_users"], st["n_items"]) == (g["n_users"], g["n_items"])
+    for k in ("a_theta", "b_theta", "a_beta", "b_beta", "a_phi", "b_phi", "a_psi", "b_psi", "E_theta", "E_beta", "E_phi", "E_psi"):
+        assert rel_max(st[k], g[k]) < TIGHT, k
+    empty = np.bincount(g["u"], minlength=g["n_users"]) == 0
+    assert empty.any() and not np.allclose(g["E_theta"][empty], g["a0"] / g["b0"]), "fixture must cover the empty-row quirk"
+    pred = O.poisson_ext_predict(g["val_u"], g["val_i"], st)
+    assert rel_max(pred, g["val_pred"]) < TIGHT and (pred[:5] == 0).all()
+    assert abs(O.rmse(g["val_x"], pred) - g["val_rmse"]) < TIGHT * g["val_rmse"]
+
+
 def test_hpf_sweeps(golden):
     g = golden("hpf_cavi")
     cfg = {k: g[k] for k in ("a", "a_prime", "b_prime", "c", "c_prime", "d_prime")}
