@@ -71,3 +71,25 @@ def test_full_size_properties(name):
     assert torch.allclose(e.rate_xi, HP["b_prime"] + e.E_theta[:, :K].sum(1), rtol=2e-6)
     assert torch.allclose(e.E_theta[:, :K], e.shp_theta[:, :K] / e.rte_theta[:, :K], rtol=1e-6)
     assert torch.all(e.E_theta[:, K:] == 0) and torch.all(e.E_beta[:, K:] == 0)      # padding never leaks
+
+
+def test_full_size_topn_c4():
+    """BASELINE configs[3] scoring shape (K=100, 230k items, top 50): the fused tcgen05 path must return exactly what
+    (i) the oracle returns for a handful of rows and (ii) the independent exact CUDA-core path returns for 1024 rows;
+    and every returned list must be sorted by (score desc, index asc) with in-range, distinct items."""
+    from oracle import pmf_oracle as O
+    from prob_matrix_factorization_b200.scoring import top_n
+    M, K, n, B = 230_000, 100, 50, 4096
+    rng = np.random.default_rng(2026)
+    Fu = rng.gamma(0.3, 1.0, (B, K)).astype(np.float32)
+    Fi = rng.gamma(0.3, 1.0, (M, K)).astype(np.float32)
+    Fi[1000:1040] = Fi[7]                                          # a block of exact ties at full size
+    idx, score, stats = top_n(Fu, Fi, n, tensor_cores=True, return_stats=True)
+    assert stats["exact_fallback_rows"] == 0
+    rows = np.array([0, 1, 17, 255, 256, 2047, 4095])
+    ref_idx, ref_score = O.topn(Fu, Fi, n, user_rows=rows)
+    assert np.array_equal(idx[rows], ref_idx) and np.array_equal(score[rows], ref_score)
+    ex_idx, ex_score = top_n(Fu[:1024], Fi, n, tensor_cores=False)
+    assert np.array_equal(idx[:1024], ex_idx) and np.array_equal(score[:1024], ex_score)
+    assert idx.min() >= 0 and idx.max() < M
+    assert np.all((np.diff(score, axis=1) < 0) | ((np.diff(score, axis=1) == 0) & (np.diff(idx, axis=1) > 0)))
