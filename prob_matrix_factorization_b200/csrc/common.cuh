@@ -64,6 +64,9 @@ struct CsrView {
     const int32_t *row_ptr, *col;
     const float* val;
     const int32_t *seg_row, *seg_start, *seg_partial, *seg_order, *row_seg, *multi_row, *multi_first;
+    // segments in processing order (longest first), one 16-byte record each: {row, first observation, one past the last
+    // observation, partial-sum slot or -1} -- what a lane group needs to start, in ONE load instead of a chain of three
+    const int4* seg_desc;
 };
 CsrView csr_view(const pmf_csr* c);
 

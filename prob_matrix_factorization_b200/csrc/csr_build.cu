@@ -329,6 +329,7 @@ struct pmf_csr {
     float* val = nullptr;
     int32_t *seg_row = nullptr, *seg_start = nullptr, *seg_partial = nullptr;
     int32_t* seg_order = nullptr;  // segment ids, longest first: a warp's groups get equally long segments
+    int4* seg_desc = nullptr;      // [n_seg] {row, start, end, partial slot} in seg_order order
     int32_t* row_seg = nullptr;    // [n_rows+1] first segment of each row
     int32_t *multi_row = nullptr, *multi_first = nullptr;
     int64_t bytes = 0;
@@ -343,6 +344,16 @@ static int dev_alloc(void** p, int64_t bytes, pmf_csr* c) {
     }
     c->bytes += bytes;
     return PMF_OK;
+}
+
+__global__ void seg_pack_kernel(const int32_t* __restrict__ seg_order, const int32_t* __restrict__ seg_row,
+                                const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_partial,
+                                const int32_t* __restrict__ row_ptr, int32_t n_seg, int32_t seg_len, int4* __restrict__ out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_seg) return;
+    const int sidx = seg_order[g];
+    const int row = seg_row[sidx], p = seg_start[sidx];
+    out[g] = make_int4(row, p, min(p + seg_len, row_ptr[row + 1]), seg_partial[sidx]);
 }
 
 // Builds seg_* / multi_* for c (row_ptr must be final).  Synchronises the stream.
@@ -393,6 +404,12 @@ static int build_segments(pmf_csr* c, cudaStream_t s) {
         PMF_TRY(stable_sort_by_key(key, c->n_seg, bit_length(c->seg_len), sorted, c->seg_order, s));
         free_async(key, s);
         free_async(sorted, s);
+    }
+    PMF_TRY(dev_alloc((void**)&c->seg_desc, (int64_t)c->n_seg * 16, c));
+    if (c->n_seg > 0) {
+        seg_pack_kernel<<<(unsigned)cdiv(c->n_seg, 256), 256, 0, s>>>(c->seg_order, c->seg_row, c->seg_start, c->seg_partial,
+                                                                      c->row_ptr, c->n_seg, c->seg_len, c->seg_desc);
+        PMF_LAUNCH_CHECK();
     }
     PMF_CUDA(cudaStreamSynchronize(s));
     return PMF_OK;
@@ -456,7 +473,7 @@ int pmf_row_stride(int K) { return K <= 0 ? 0 : ((K + 7) / 8) * 8; }
 
 int pmf_csr_free(pmf_csr* c) {
     if (!c) return PMF_OK;
-    void* ptrs[] = {c->row_ptr, c->perm, c->col, c->val, c->seg_row, c->seg_start, c->seg_partial, c->seg_order,
+    void* ptrs[] = {c->seg_desc, c->row_ptr, c->perm, c->col, c->val, c->seg_row, c->seg_start, c->seg_partial, c->seg_order,
                     c->row_seg, c->multi_row, c->multi_first};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -597,6 +614,6 @@ namespace pmf {
 CsrView csr_view(const pmf_csr* c) {
     return CsrView{c->nnz, c->n_rows, c->row_offset, c->seg_len, c->n_seg, c->n_multi, c->n_partial, c->row_ptr,
                    c->col, c->val, c->seg_row, c->seg_start, c->seg_partial, c->seg_order, c->row_seg,
-                   c->multi_row, c->multi_first};
+                   c->multi_row, c->multi_first, c->seg_desc};
 }
 }  // namespace pmf

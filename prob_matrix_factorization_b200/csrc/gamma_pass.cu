@@ -30,10 +30,12 @@ namespace pmf {
 constexpr int kMaxPeers = 7;   // 8 GPUs per NVSwitch domain
 
 struct GammaArgs {
-    const int32_t *seg_row, *seg_start, *seg_partial, *seg_order, *row_ptr, *col;
+    const int4* seg_desc;   // segments in processing order: {row, start, end, partial slot or -1}
+    const int32_t* col;
     const float* val;
     const int32_t *multi_row, *multi_first;
     int32_t n_seg, n_multi, seg_len, row_offset, K, ld, nvec;
+    int64_t nnz_hint;   // observations of this rating list (dispatch heuristics only)
     const float* E_oth;
     float* E_self;
     float* shp;
@@ -151,11 +153,8 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
     int row = 0, p = 0, end = 0, pidx = -1;
     if (has) {
         // segments are visited longest first, so the groups sharing a warp run (nearly) equal trip counts
-        const int sidx = a.seg_order[gid];
-        row = a.seg_row[sidx];
-        p = a.seg_start[sidx];
-        end = min(p + a.seg_len, a.row_ptr[row + 1]);
-        pidx = a.seg_partial[sidx];
+        const int4 d = __ldg(a.seg_desc + gid);
+        row = d.x; p = d.y; end = d.z; pidx = d.w;
     }
     const int R = a.row_offset + row;
     float4 self[V], sa[V], sb[V];
@@ -183,6 +182,7 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
         const int rem = end - (p + base);
 #pragma unroll
         for (int j0 = 0; j0 < G; j0 += U) {
+            if (U < G && j0 >= maxlen - base) break;   // warp-uniform: nobody in the warp has observations left
             float4 o[U][V];
             float so[U];   // MODE 2: the gathered rows' scalars
 #pragma unroll
@@ -362,22 +362,29 @@ static int launch_gamma(const GammaArgs& a_in, int mode, cudaStream_t s) {
 }
 
 static void fill_csr_args(GammaArgs& a, const CsrView& c, int32_t K, int32_t ld) {
-    a.seg_row = c.seg_row; a.seg_start = c.seg_start; a.seg_partial = c.seg_partial; a.seg_order = c.seg_order;
-    a.row_ptr = c.row_ptr;
+    a.seg_desc = c.seg_desc;
     a.col = c.col; a.val = c.val; a.multi_row = c.multi_row; a.multi_first = c.multi_first;
     a.n_seg = c.n_seg; a.n_multi = c.n_multi; a.seg_len = c.seg_len; a.row_offset = c.row_offset;
-    a.K = K; a.ld = ld; a.nvec = ld / 4;
+    a.K = K; a.ld = ld; a.nvec = ld / 4; a.nnz_hint = c.nnz;
     a.scale_oth = nullptr; a.scale_shp = nullptr; a.partial_x = nullptr;
 }
 
 static int dispatch_gamma(const GammaArgs& a, int mode, cudaStream_t s) {
     const int nv = a.nvec;
+    // U = gathered rows in flight per lane.  Long segments (C5: 50-200 ratings per row) want 8; when the average segment
+    // is shorter than a lane group's chunk of 8, U = 2 wins: 40 fewer registers (3 CTAs per SM instead of 2, the pass is
+    // latency-bound on short rows) and the chunk loop stops as soon as no group of the warp has ratings left
+    // (C2/C3: 0.31 -> 0.27 ms per sweep, profiles/README.md).
+    const bool short_segments = g_tune_unroll == 0 && a.n_seg > 0 && a.nnz_hint / a.n_seg < 8;
     if (nv <= 4) return launch_gamma<4, 1, 4>(a, mode, s);
-    if (nv <= 8) return g_tune_unroll == 4 ? launch_gamma<8, 1, 4>(a, mode, s) : launch_gamma<8, 1, 8>(a, mode, s);
+    if (nv <= 8) {
+        if (g_tune_unroll == 2 || short_segments) return launch_gamma<8, 1, 2>(a, mode, s);
+        return g_tune_unroll == 4 ? launch_gamma<8, 1, 4>(a, mode, s) : launch_gamma<8, 1, 8>(a, mode, s);
+    }
     if (nv <= 16) {
         if (g_tune_group == 16) return g_tune_unroll == 8 ? launch_gamma<16, 1, 8>(a, mode, s) : launch_gamma<16, 1, 4>(a, mode, s);
         if (g_tune_unroll == 4) return launch_gamma<8, 2, 4>(a, mode, s);
-        if (g_tune_unroll == 2) return launch_gamma<8, 2, 2>(a, mode, s);
+        if (g_tune_unroll == 2 || short_segments) return launch_gamma<8, 2, 2>(a, mode, s);
         return launch_gamma<8, 2, 8>(a, mode, s);   // measured best on C5 (profiles/README.md)
     }
     if (nv <= 24) return launch_gamma<8, 3, 2>(a, mode, s);
