@@ -218,6 +218,8 @@ int pmf_eval_stats(const int32_t* d_users, const int32_t* d_items, const float* 
  * its own bias on the self side).  d_workspace: pmf_gauss_workspace_bytes() bytes.
  * pmf_gauss_bias_pass replaces :206-232 / :237-263:
  *     b_self[R] = sum_t (val_t - b_oth[col_t] - <m_self[R], m_oth[col_t]>) / sigma2 / (1/eta_b2 + n_R/sigma2)
+ * (float64 residual sums per segment, combined per row in segment order; d_workspace: the same
+ * pmf_gauss_workspace_bytes() buffer, 8-byte aligned, free to reuse between the passes).
  */
 int pmf_gauss_packed_stride(int K);
 int64_t pmf_gauss_workspace_bytes(const pmf_csr* csr, int32_t K);
@@ -225,7 +227,7 @@ int pmf_gauss_factor_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, c
                           const float* d_b_oth, float* d_m_self, float* d_V_self, float* d_Q_self,
                           const float* d_b_self, float sigma2, float eta2, void* d_workspace, void* stream);
 int pmf_gauss_bias_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_m_self,
-                        const float* d_b_oth, float* d_b_self, float sigma2, float eta_b2, void* stream);
+                        const float* d_b_oth, float* d_b_self, float sigma2, float eta_b2, void* d_workspace, void* stream);
 
 /* ---- a6/a7: gradient-based HPF (HPF_PyTorch) ----------------------------------------------
  * Parameters keep the reference's shapes (hpf_pytorch.py:39-48): theta_raw (N,K), beta_raw (M,K) row-major

@@ -176,25 +176,28 @@ __global__ void __launch_bounds__(kSolveThreads) gauss_solve_kernel(const GaussA
     }
 }
 
-// Bias pass: one warp per row; 8 lanes per rating compute <m_self[row], m_oth[col]> (float64 accumulate).
+// Bias pass (gaussian_mf_cavi_bias.py:206-263), two kernels so that a row with thousands of ratings is not walked by one
+// warp: (1) one warp per SEGMENT (<= seg_len ratings), 8 lanes per rating compute <m_self[row], m_oth[col]> and the
+// segment's residual sum in float64; (2) one thread per row adds its segments' sums in segment order (deterministic)
+// and applies the update.
 struct BiasArgs {
-    const int32_t *row_ptr, *col;
+    const int32_t *row_ptr, *col, *seg_row, *seg_start, *row_seg;
     const float* val;
-    int32_t n_rows, row_offset, ld, nvec;
+    int32_t n_rows, n_seg, seg_len, row_offset, ld, nvec;
     const float *m_self, *m_oth, *b_oth;
     float* b_self;
     float sigma2, eta_b2;
+    double* partial;   // [n_seg]
 };
 
-__global__ void __launch_bounds__(256) gauss_bias_kernel(const BiasArgs a) {
+__global__ void __launch_bounds__(256) gauss_bias_partial_kernel(const BiasArgs a) {
     const int lane = threadIdx.x & 31, gl = lane & 7, grp = lane >> 3;
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (wid >= a.n_rows) return;
-    const int row = (int)wid;
-    const int p0 = a.row_ptr[row], p1 = a.row_ptr[row + 1];
-    if (p0 == p1) return;  // gaussian_mf_cavi_bias.py:208-209
-    const size_t R = (size_t)(a.row_offset + row);
-    const float* own = a.m_self + R * a.ld;
+    if (wid >= a.n_seg) return;
+    const int row = a.seg_row[wid];
+    const int p0 = a.seg_start[wid];
+    const int p1 = min(p0 + a.seg_len, a.row_ptr[row + 1]);
+    const float* own = a.m_self + (size_t)(a.row_offset + row) * a.ld;
     double acc = 0.0;
     for (int base = p0; base < p1; base += 4) {
         const int p = base + grp;
@@ -215,10 +218,18 @@ __global__ void __launch_bounds__(256) gauss_bias_kernel(const BiasArgs a) {
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 8);
     acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-    if (lane == 0) {
-        const double prec = 1.0 / (double)a.eta_b2 + (double)(p1 - p0) / (double)a.sigma2;   // :226
-        a.b_self[R] = (float)((1.0 / prec) / (double)a.sigma2 * acc);                          // :230
-    }
+    if (lane == 0) a.partial[wid] = acc;
+}
+
+__global__ void __launch_bounds__(256) gauss_bias_finish_kernel(const BiasArgs a) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= a.n_rows) return;
+    const int n = a.row_ptr[row + 1] - a.row_ptr[row];
+    if (n == 0) return;  // gaussian_mf_cavi_bias.py:208-209
+    double acc = 0.0;
+    for (int sg = a.row_seg[row]; sg < a.row_seg[row + 1]; ++sg) acc += a.partial[sg];
+    const double prec = 1.0 / (double)a.eta_b2 + (double)n / (double)a.sigma2;          // :226
+    a.b_self[a.row_offset + row] = (float)((1.0 / prec) / (double)a.sigma2 * acc);     // :230
 }
 
 }  // namespace pmf
@@ -278,19 +289,27 @@ int pmf_gauss_factor_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, c
 }
 
 int pmf_gauss_bias_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_m_self,
-                        const float* d_b_oth, float* d_b_self, float sigma2, float eta_b2, void* stream) {
+                        const float* d_b_oth, float* d_b_self, float sigma2, float eta_b2, void* d_workspace, void* stream) {
     PMF_REQUIRE(csr != nullptr, "csr is NULL");
     PMF_REQUIRE(K >= 1, "K must be positive");
-    PMF_REQUIRE(d_m_oth && d_m_self && d_b_oth && d_b_self, "NULL table");
+    PMF_REQUIRE(d_m_oth && d_m_self && d_b_oth && d_b_self && d_workspace, "NULL table");
+    PMF_REQUIRE(((uintptr_t)d_workspace & 7) == 0, "workspace must be 8-byte aligned");
     PMF_REQUIRE(sigma2 > 0.f && eta_b2 > 0.f, "variances must be positive");
     const CsrView c = csr_view(csr);
     BiasArgs a;
-    a.row_ptr = c.row_ptr; a.col = c.col; a.val = c.val; a.n_rows = c.n_rows; a.row_offset = c.row_offset;
+    a.row_ptr = c.row_ptr; a.col = c.col; a.val = c.val; a.seg_row = c.seg_row; a.seg_start = c.seg_start; a.row_seg = c.row_seg;
+    a.n_rows = c.n_rows; a.n_seg = c.n_seg; a.seg_len = c.seg_len; a.row_offset = c.row_offset;
     a.ld = pmf_row_stride(K); a.nvec = a.ld / 4;
     a.m_self = d_m_self; a.m_oth = d_m_oth; a.b_oth = d_b_oth; a.b_self = d_b_self;
     a.sigma2 = sigma2; a.eta_b2 = eta_b2;
+    a.partial = (double*)d_workspace;   // n_seg doubles <= pmf_gauss_workspace_bytes (>= 8 floats per segment)
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c.n_seg > 0) {
+        gauss_bias_partial_kernel<<<(unsigned)cdiv((int64_t)c.n_seg * 32, 256), 256, 0, s>>>(a);
+        PMF_LAUNCH_CHECK();
+    }
     if (c.n_rows > 0) {
-        gauss_bias_kernel<<<(unsigned)cdiv((int64_t)c.n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(a);
+        gauss_bias_finish_kernel<<<(unsigned)cdiv(c.n_rows, 256), 256, 0, s>>>(a);
         PMF_LAUNCH_CHECK();
     }
     return PMF_OK;

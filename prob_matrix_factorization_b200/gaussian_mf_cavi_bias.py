@@ -98,9 +98,9 @@ class GaussEngine:
               p(self.m_beta), p(self.V_beta), p(self.Q_beta), p(self.b_item), sigma2, eta_beta2, p(self.ws_item), st())
             if self.bias:
                 c("pmf_gauss_bias_pass", self.r.by_user.handle, self.K, p(self.m_beta), p(self.m_theta), p(self.b_item),
-                  p(self.b_user), sigma2, eta_bias2, st())
+                  p(self.b_user), sigma2, eta_bias2, p(self.ws_user), st())
                 c("pmf_gauss_bias_pass", self.r.by_item.handle, self.K, p(self.m_theta), p(self.m_beta), p(self.b_user),
-                  p(self.b_item), sigma2, eta_bias2, st())
+                  p(self.b_item), sigma2, eta_bias2, p(self.ws_item), st())
 
 
 class GaussianMFCAVI(_DeviceBacked):
