@@ -72,107 +72,112 @@ __global__ void gauss_accumulate_kernel(const GaussArgs a) {
     }
 }
 
-constexpr int kSolveThreads = 64;
+// packed lower-triangle index e -> (i, j), j <= i
+__device__ __forceinline__ void unpack_tri(int e, int& i, int& j) {
+    i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+    while ((i + 1) * (i + 2) / 2 <= e) ++i;
+    while (i * (i + 1) / 2 > e) --i;
+    j = e - i * (i + 1) / 2;
+}
 
-// One CTA per row.  Shared: A[K][K+1] float64 (P, then L, then L^-1), rhs[K], mean[K].
-__global__ void __launch_bounds__(kSolveThreads) gauss_solve_kernel(const GaussArgs a) {
+// 1/sqrt(d) in float64: float estimate + two Newton steps (relative error ~1e-16; the results are stored as float32)
+__device__ __forceinline__ double rsqrt64(double d) {
+    double y = (double)rsqrtf((float)d);
+    y = y * (1.5 - 0.5 * d * y * y);
+    y = y * (1.5 - 0.5 * d * y * y);
+    return y;
+}
+
+// One WARP per row (several rows per CTA, no block-wide barriers).  Shared, per warp, float64:
+// A[K][K+1] (P, then L below / L^-1 above the diagonal, then V below), rinv[K] (1/L_kk, later diag V), rhs[K], mean[K].
+__global__ void __launch_bounds__(256) gauss_solve_kernel(const GaussArgs a) {
     extern __shared__ double sm[];
     const int K = a.K, LD = K + 1;
-    double* A = sm;
-    double* rhs = A + (size_t)K * LD;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= a.n_rows) return;
+    if (a.row_ptr[row + 1] == a.row_ptr[row]) return;  // no ratings: keep the state (:134-135)
+    double* A = sm + (size_t)warp * ((size_t)K * LD + 3 * K);
+    double* rinv = A + (size_t)K * LD;
+    double* rhs = rinv + K;
     double* mean = rhs + K;
-    const int row = blockIdx.x;
     const int s0 = a.row_seg[row], s1 = a.row_seg[row + 1];
-    if (a.row_ptr[row + 1] == a.row_ptr[row]) return;  // no ratings: keep the state
-    const int tid = threadIdx.x;
     const int W = a.ldq + a.ld;
     const int npk = K * (K + 1) / 2;
-    // P = I/eta2 + S/sigma2 (lower triangle), rhs = sum res*m
-    for (int e = tid; e < npk + K; e += kSolveThreads) {
+    const double inv_sigma2 = 1.0 / (double)a.sigma2, inv_eta2 = 1.0 / (double)a.eta2;
+    // P = I/eta2 + S/sigma2 (lower triangle), rhs = sum res*m; the segments' sums are added in segment order
+    for (int e = lane; e < npk + K; e += 32) {
         const int off = e < npk ? e : a.ldq + (e - npk);
         double s = 0.0;
         for (int sg = s0; sg < s1; ++sg) s += (double)a.scratch[(size_t)sg * W + off];
         if (e < npk) {
-            int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-            while ((i + 1) * (i + 2) / 2 <= e) ++i;
-            while (i * (i + 1) / 2 > e) --i;
-            const int j = e - i * (i + 1) / 2;
-            A[i * LD + j] = s / (double)a.sigma2 + (i == j ? 1.0 / (double)a.eta2 : 0.0);
+            int i, j;
+            unpack_tri(e, i, j);
+            A[i * LD + j] = s * inv_sigma2 + (i == j ? inv_eta2 : 0.0);
         } else {
             rhs[e - npk] = s;
         }
     }
-    __syncthreads();
-    // Cholesky P = L L^T, in place in the lower triangle
+    __syncwarp();
+    // Cholesky P = L L^T, left-looking by columns: every lane recomputes the pivot (k multiply-adds, no exchange),
+    // lane i finishes L[i][k] for its rows i > k.  L[k][j], j < k, was completed in earlier columns.
     for (int k = 0; k < K; ++k) {
-        if (tid == 0) A[k * LD + k] = sqrt(A[k * LD + k]);
-        __syncthreads();
-        const double d = A[k * LD + k];
-        for (int i = k + 1 + tid; i < K; i += kSolveThreads) A[i * LD + k] /= d;
-        __syncthreads();
-        // trailing update of the lower triangle: A[i][j] -= A[i][k] A[j][k] for k < j <= i
-        const int n = K - k - 1;
-        for (int e = tid; e < n * n; e += kSolveThreads) {
-            const int i = k + 1 + e / n, j = k + 1 + e % n;
-            if (j <= i) A[i * LD + j] -= A[i * LD + k] * A[j * LD + k];
+        double d = A[k * LD + k];
+        for (int j = 0; j < k; ++j) d -= A[k * LD + j] * A[k * LD + j];
+        const double rk = rsqrt64(d);
+        for (int i = k + 1 + lane; i < K; i += 32) {
+            double t = A[i * LD + k];
+            for (int j = 0; j < k; ++j) t -= A[i * LD + j] * A[k * LD + j];
+            A[i * LD + k] = t * rk;
         }
-        __syncthreads();
+        __syncwarp();              // everybody has read the old A[k][k]
+        if (lane == 0) { A[k * LD + k] = d * rk; rinv[k] = rk; }
+        __syncwarp();
     }
-    // L^-1 column by column (thread c owns column c), stored in the strict upper part + diagonal copy:
-    // we overwrite A's upper triangle U[c][i] (row c, col i >= c) with Linv[i][c].
-    for (int c = tid; c < K; c += kSolveThreads) {
-        // forward substitution L x = e_c ; x_i = 0 for i < c
-        double* x = A + (size_t)c * LD;  // row c, entries c..K-1 of the UPPER triangle hold x_c..x_{K-1}
-        // careful: A[c][c] holds L[c][c]; compute x_c first into a register and write it last
-        const double xc = 1.0 / A[c * LD + c];
+    // L^-1 column by column (lane c owns column c): x_c = 1/L_cc, x_i = -(sum_{c<=j<i} L_ij x_j)/L_ii, stored in row c of
+    // the UPPER triangle (A[c][i] = Linv[i][c], i > c); the diagonal follows after everybody is done reading L.
+    for (int c = lane; c < K; c += 32) {
+        double* x = A + (size_t)c * LD;
+        const double xc = rinv[c];
         for (int i = c + 1; i < K; ++i) {
-            double s = A[i * LD + c] * xc;  // L[i][c] * x_c
-            for (int j = c + 1; j < i; ++j) s += A[i * LD + j] * x[j];   // L[i][j] * x_j (x_j in row c, col j)
-            x[i] = -s / A[i * LD + i];
+            double s = A[i * LD + c] * xc;
+            for (int j = c + 1; j < i; ++j) s += A[i * LD + j] * x[j];
+            x[i] = -s * rinv[i];
         }
-        mean[c] = xc;  // stash x_c (the diagonal still holds L[c][c] for the other threads)
+        mean[c] = xc;
     }
-    __syncthreads();
-    for (int c = tid; c < K; c += kSolveThreads) A[c * LD + c] = mean[c];
-    __syncthreads();
-    // now Linv[i][c] = A[c][i] for i >= c.  V = Linv^T Linv: V[i][j] = sum_{k >= max(i,j)} Linv[k][i] Linv[k][j]
-    // write V (packed, float32) and keep a float64 copy of the lower triangle in A[i][j], i > j.
-    const size_t R = (size_t)(a.row_offset + row);
-    for (int e = tid; e < npk; e += kSolveThreads) {
-        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-        while ((i + 1) * (i + 2) / 2 <= e) ++i;
-        while (i * (i + 1) / 2 > e) --i;
-        const int j = e - i * (i + 1) / 2;  // j <= i
+    __syncwarp();
+    for (int c = lane; c < K; c += 32) A[c * LD + c] = mean[c];
+    __syncwarp();
+    // V = Linv^T Linv: V[i][j] = sum_{k >= i} Linv[k][i] Linv[k][j] (j <= i) = sum_k A[i][k] A[j][k]; strictly-lower entries
+    // overwrite L (no longer needed), the diagonal goes to rinv[]
+    for (int e = lane; e < npk; e += 32) {
+        int i, j;
+        unpack_tri(e, i, j);
         double s = 0.0;
         for (int k = i; k < K; ++k) s += A[i * LD + k] * A[j * LD + k];
-        // stash: strictly-lower entries go to A[i][j]; the diagonal to rhs-sized buffer later
-        if (i != j) A[i * LD + j] = s; else mean[i] = s;  // mean[] reused as diag(V) (x_c already copied)
+        if (i != j) A[i * LD + j] = s; else rinv[i] = s;
     }
-    __syncthreads();
-    // m = V rhs / sigma2 (thread per row of V)
-    double mi = 0.0;
-    const bool own = tid < K;
-    for (int i = tid; i < K; i += kSolveThreads) {
-        double s = mean[i] * rhs[i];
+    __syncwarp();
+    // m = V rhs / sigma2
+    const size_t R = (size_t)(a.row_offset + row);
+    for (int i = lane; i < K; i += 32) {
+        double s = rinv[i] * rhs[i];
         for (int j = 0; j < K; ++j) {
             if (j == i) continue;
-            const double vij = j < i ? A[i * LD + j] : A[j * LD + i];
-            s += vij * rhs[j];
+            s += (j < i ? A[i * LD + j] : A[j * LD + i]) * rhs[j];
         }
-        mi = s / (double)a.sigma2;
+        const double mi = s * inv_sigma2;
         a.m_self[R * a.ld + i] = (float)mi;
-        A[i * LD + K] = mi;  // column K of row i: the new mean (float64) for Q below
+        mean[i] = mi;
     }
-    (void)own;
-    __syncthreads();
-    for (int e = tid; e < npk; e += kSolveThreads) {
-        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-        while ((i + 1) * (i + 2) / 2 <= e) ++i;
-        while (i * (i + 1) / 2 > e) --i;
-        const int j = e - i * (i + 1) / 2;
-        const double v = (i == j) ? mean[i] : A[i * LD + j];
+    __syncwarp();
+    for (int e = lane; e < npk; e += 32) {
+        int i, j;
+        unpack_tri(e, i, j);
+        const double v = (i == j) ? rinv[i] : A[i * LD + j];
         a.V_self[R * a.ldq + e] = (float)v;
-        a.Q_self[R * a.ldq + e] = (float)(v + A[i * LD + K] * A[j * LD + K]);   // E[th th^T], :151 / :187
+        a.Q_self[R * a.ldq + e] = (float)(v + mean[i] * mean[j]);   // E[th th^T], :151 / :187
     }
 }
 
@@ -279,10 +284,13 @@ int pmf_gauss_factor_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, c
         PMF_LAUNCH_CHECK();
     }
     if (c.n_rows > 0) {
-        const size_t smem = ((size_t)K * (K + 1) + 2 * (size_t)K) * sizeof(double);
+        const size_t per_warp = ((size_t)K * (K + 1) + 3 * (size_t)K) * sizeof(double);
+        int warps = (int)((size_t)(96 * 1024) / per_warp);       // rows per CTA: as many as fit in 96 KB, at most 8
+        warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
+        const size_t smem = per_warp * warps;
         if (smem > 48 * 1024)
             PMF_CUDA(cudaFuncSetAttribute(gauss_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gauss_solve_kernel<<<c.n_rows, kSolveThreads, smem, s>>>(a);
+        gauss_solve_kernel<<<(unsigned)cdiv(c.n_rows, warps), 32 * warps, smem, s>>>(a);
         PMF_LAUNCH_CHECK();
     }
     return PMF_OK;
