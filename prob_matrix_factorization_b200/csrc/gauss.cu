@@ -24,6 +24,7 @@ namespace pmf {
 
 struct GaussArgs {
     const int32_t *seg_row, *seg_start, *seg_order, *row_ptr, *row_seg, *col;
+    const int4* seg_desc;
     const float* val;
     int32_t n_seg, n_rows, seg_len, row_offset, K, ld, ldq, nq4, nm4;
     const float *m_oth, *Q_oth, *b_oth, *b_self;
@@ -34,10 +35,9 @@ struct GaussArgs {
 
 template <int V>
 __global__ void gauss_accumulate_kernel(const GaussArgs a) {
-    const int sidx = a.seg_order[blockIdx.x];
-    const int row = a.seg_row[sidx];
-    const int p0 = a.seg_start[sidx];
-    const int p1 = min(p0 + a.seg_len, a.row_ptr[row + 1]);
+    const int sidx = a.seg_order[blockIdx.x];            // scratch is indexed by segment id, not by processing order
+    const int4 d = __ldg(a.seg_desc + blockIdx.x);       // {row, start, end, .}
+    const int row = d.x, p0 = d.y, p1 = d.z;
     const int T = blockDim.x;
     const int nslots = a.nq4 + a.nm4;
     const float bs = a.b_self ? a.b_self[a.row_offset + row] : 0.f;
@@ -264,7 +264,7 @@ int pmf_gauss_factor_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, c
     const CsrView c = csr_view(csr);
     GaussArgs a;
     a.seg_row = c.seg_row; a.seg_start = c.seg_start; a.seg_order = c.seg_order; a.row_ptr = c.row_ptr;
-    a.row_seg = c.row_seg; a.col = c.col; a.val = c.val;
+    a.row_seg = c.row_seg; a.col = c.col; a.val = c.val; a.seg_desc = c.seg_desc;
     a.n_seg = c.n_seg; a.n_rows = c.n_rows; a.seg_len = c.seg_len; a.row_offset = c.row_offset;
     a.K = K; a.ld = pmf_row_stride(K); a.ldq = pmf_gauss_packed_stride(K); a.nq4 = a.ldq / 4; a.nm4 = a.ld / 4;
     a.m_oth = d_m_oth; a.Q_oth = d_Q_oth; a.b_oth = d_b_oth; a.b_self = d_b_self;

@@ -29,7 +29,8 @@ __global__ void geomean_kernel(const float* __restrict__ shp, const float* __res
 }
 
 struct DigammaArgs {
-    const int32_t *seg_row, *seg_start, *seg_partial, *seg_order, *row_ptr, *col, *multi_row, *multi_first;
+    const int4* seg_desc;
+    const int32_t *col, *multi_row, *multi_first;
     const float* val;
     int32_t n_seg, n_multi, seg_len, row_offset, K, ld, nvec;
     const float *G_oth, *E_oth;
@@ -92,11 +93,8 @@ __global__ void __launch_bounds__(256) digamma_pass_kernel(const DigammaArgs a) 
     const bool has = gid < a.n_seg;
     int row = 0, p = 0, end = 0, pidx = -1;
     if (has) {
-        const int sidx = a.seg_order[gid];
-        row = a.seg_row[sidx];
-        p = a.seg_start[sidx];
-        end = min(p + a.seg_len, a.row_ptr[row + 1]);
-        pidx = a.seg_partial[sidx];
+        const int4 d = __ldg(a.seg_desc + gid);   // {row, start, end, partial slot}: one load, not a chain of three
+        row = d.x; p = d.y; end = d.z; pidx = d.w;
     }
     const int R = a.row_offset + row;
     float4 self[V], sa[V], sb[V];
@@ -321,8 +319,7 @@ int pmf_gamma_pass_digamma(const pmf_csr* csr, int32_t K, int32_t ld, const floa
     const CsrView c = csr_view(csr);
     PMF_REQUIRE(c.n_partial == 0 || d_workspace != nullptr, "workspace is NULL");
     DigammaArgs a;
-    a.seg_row = c.seg_row; a.seg_start = c.seg_start; a.seg_partial = c.seg_partial; a.seg_order = c.seg_order;
-    a.row_ptr = c.row_ptr; a.col = c.col; a.val = c.val; a.multi_row = c.multi_row; a.multi_first = c.multi_first;
+    a.seg_desc = c.seg_desc; a.col = c.col; a.val = c.val; a.multi_row = c.multi_row; a.multi_first = c.multi_first;
     a.n_seg = c.n_seg; a.n_multi = c.n_multi; a.seg_len = c.seg_len; a.row_offset = c.row_offset;
     a.K = K; a.ld = ld; a.nvec = ld / 4;
     a.G_oth = d_G_oth; a.E_oth = d_E_oth; a.G_self = d_G_self; a.E_self = d_E_self; a.shp = d_shp; a.rte = d_rte;

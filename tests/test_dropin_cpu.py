@@ -10,6 +10,7 @@ import pytest
 
 REF = os.environ.get("PMF_REFERENCE_ROOT", "/root/reference")
 PAIRS = [("poisson_mf_cavi", "PoissonMFCAVIConfig", "PoissonMFCAVI"), ("hpf_cavi", "HPF_CAVI_Config", "HPF_CAVI"),
+         ("poisson_mf_extended_cavi", "PoissonMFExtendedCAVIConfig", "PoissonMFExtendedCAVI"),
          ("gaussian_mf_cavi", "GaussianMFCAVIConfig", "GaussianMFCAVI"),
          ("gaussian_mf_cavi_bias", "GaussianMFCAVIConfig", "GaussianMFCAVI"),
          ("hpf_pytorch", "HPF_PyTorch_Config", "HPF_PyTorch")]
@@ -24,6 +25,7 @@ def test_install_routes_reference_import_paths():
         from src.models.hpf_cavi import HPF_CAVI, HPF_CAVI_Config  # noqa: F401
         from src.models.gaussian_mf_cavi_bias import GaussianMFCAVI, GaussianMFCAVIConfig  # noqa: F401
         from src.models.hpf_pytorch import HPF_PyTorch, HPF_PyTorch_Config  # noqa: F401
+        from src.models.poisson_mf_extended_cavi import PoissonMFExtendedCAVI, PoissonMFExtendedCAVIConfig  # noqa: F401
         from src.evaluation.metrics import rmse, macro_mae  # noqa: F401
         assert PoissonMFCAVI.__module__.startswith("prob_matrix_factorization_b200")
         assert HPF_PyTorch.__module__.startswith("prob_matrix_factorization_b200")
