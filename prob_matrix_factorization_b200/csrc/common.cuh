@@ -67,6 +67,7 @@ struct CsrView {
     // segments in processing order (longest first), one 16-byte record each: {row, first observation, one past the last
     // observation, partial-sum slot or -1} -- what a lane group needs to start, in ONE load instead of a chain of three
     const int4* seg_desc;
+    int32_t n_cols;   // 1 + largest id of the other side in `col` (extent of the gathered table that can be touched)
 };
 CsrView csr_view(const pmf_csr* c);
 

@@ -253,8 +253,14 @@ __global__ void gather_kernel(const int32_t* __restrict__ perm, const int32_t* _
 __global__ void check_keys_kernel(const int32_t* __restrict__ key, const int32_t* __restrict__ other, int64_t n,
                                   int32_t n_rows, int32_t* __restrict__ bad) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    if (key[p] < 0 || key[p] >= n_rows || other[p] < 0) atomicOr(bad, 1);
+    int oth = -1;
+    if (p < n) {
+        oth = other[p];
+        if (key[p] < 0 || key[p] >= n_rows || oth < 0) atomicOr(bad, 1);
+    }
+    // bad[1] = largest id of the other side: how many rows of the other side's table the passes can touch
+    const int wmax = __reduce_max_sync(0xffffffffu, oth);
+    if ((threadIdx.x & 31) == 0 && wmax >= 0) atomicMax(bad + 1, wmax);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -324,6 +330,7 @@ using namespace pmf;
 struct pmf_csr {
     int64_t nnz = 0;
     int32_t n_rows = 0, row_offset = 0, seg_len = 0;
+    int32_t n_cols = 0;            // 1 + largest id of the other side seen in `col`
     int32_t n_seg = 0, n_multi = 0, n_partial = 0;
     int32_t *row_ptr = nullptr, *perm = nullptr, *col = nullptr;
     float* val = nullptr;
@@ -509,15 +516,16 @@ int pmf_csr_build(const int32_t* d_key, const int32_t* d_other, const float* d_v
     } else {
         auto body = [&]() -> int {
             int32_t* bad = nullptr;
-            PMF_TRY(alloc_async(&bad, 1, s));
-            PMF_CUDA(cudaMemsetAsync(bad, 0, 4, s));
+            PMF_TRY(alloc_async(&bad, 2, s));
+            PMF_CUDA(cudaMemsetAsync(bad, 0, 8, s));
             check_keys_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(d_key, d_other, nnz, n_rows, bad);
             PMF_LAUNCH_CHECK();
-            int32_t h_bad = 0;
-            PMF_CUDA(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, s));
+            int32_t h_bad[2] = {0, 0};
+            PMF_CUDA(cudaMemcpyAsync(h_bad, bad, 8, cudaMemcpyDeviceToHost, s));
             PMF_CUDA(cudaStreamSynchronize(s));
             free_async(bad, s);
-            PMF_REQUIRE(h_bad == 0, "ids out of range: keys must lie in [0, %d), other ids must be >= 0", n_rows);
+            PMF_REQUIRE(h_bad[0] == 0, "ids out of range: keys must lie in [0, %d), other ids must be >= 0", n_rows);
+            c->n_cols = h_bad[1] + 1;
 
             int32_t* k0 = nullptr;
             PMF_TRY(alloc_async(&k0, nnz, s));
@@ -552,6 +560,7 @@ int pmf_csr_slice(const pmf_csr* src, int32_t row_begin, int32_t row_end, void* 
     c->n_rows = row_end - row_begin;
     c->row_offset = src->row_offset + row_begin;
     c->seg_len = src->seg_len;
+    c->n_cols = src->n_cols;
     auto body = [&]() -> int {
         PMF_TRY(dev_alloc((void**)&c->row_ptr, ((int64_t)c->n_rows + 1) * 4, c));
         PMF_TRY(dev_alloc((void**)&c->perm, c->nnz * 4, c));
@@ -614,6 +623,6 @@ namespace pmf {
 CsrView csr_view(const pmf_csr* c) {
     return CsrView{c->nnz, c->n_rows, c->row_offset, c->seg_len, c->n_seg, c->n_multi, c->n_partial, c->row_ptr,
                    c->col, c->val, c->seg_row, c->seg_start, c->seg_partial, c->seg_order, c->row_seg,
-                   c->multi_row, c->multi_first, c->seg_desc};
+                   c->multi_row, c->multi_first, c->seg_desc, c->n_cols};
 }
 }  // namespace pmf

@@ -36,6 +36,7 @@ struct GammaArgs {
     const int32_t *multi_row, *multi_first;
     int32_t n_seg, n_multi, seg_len, row_offset, K, ld, nvec;
     int64_t nnz_hint;   // observations of this rating list (dispatch heuristics only)
+    int64_t gather_bytes;   // size of the part of E_oth this pass can touch (dispatch heuristics only)
     const float* E_oth;
     float* E_self;
     float* shp;
@@ -141,7 +142,7 @@ __device__ __forceinline__ void gamma_row_update(const GammaArgs& a, int R, int 
     }
 }
 
-template <int G, int V, int U, int MODE>
+template <int G, int V, int U, int MODE, bool CHUNK_REDUCE>
 __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
     static_assert(G == 4 || G == 8 || G == 16 || G == 32, "group size");
     static_assert(G % U == 0, "U must divide G");
@@ -197,6 +198,65 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
                     o[jj][v] = (j < rem && idx < a.nvec) ? ldg_f4(rowp + idx * 4) : f4_zero();
                 }
             }
+            if constexpr (CHUNK_REDUCE) {
+                // The whole chunk is in registers: reduce its G dot products TOGETHER.  A butterfly that halves the number
+                // of values per step leaves lane j with the complete dot product of rating j after G-1 shuffles (instead
+                // of log2(G) per rating), lane j -- which also loaded rating j's value -- does the ONE division, and the
+                // weights are handed back with one shuffle per rating.
+                float d[G];
+#pragma unroll
+                for (int jj = 0; jj < G; ++jj) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        t = fmaf(self[v].x, o[jj][v].x, t);
+                        t = fmaf(self[v].y, o[jj][v].y, t);
+                        t = fmaf(self[v].z, o[jj][v].z, t);
+                        t = fmaf(self[v].w, o[jj][v].w, t);
+                    }
+                    d[jj] = t;
+                }
+#pragma unroll
+                for (int h = G / 2; h > 0; h >>= 1) {
+                    const bool up = (gl & h) != 0;
+#pragma unroll
+                    for (int i = 0; i < h; ++i) {
+                        const float send = up ? d[i] : d[i + h];
+                        const float keep = up ? d[i + h] : d[i];
+                        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+                    }
+                }
+                float w_l;   // weight of rating gl of the chunk (x_l = 0 and all-zero rows past the segment end give 0)
+                if constexpr (MODE == 2) {
+                    w_l = gl < rem ? x_l / d[0] : 0.f;   // poisson_mf_extended_cavi.py:142: the raw dot product
+                    sx += x_l;                           // per-lane share; summed over the group after the loop
+                } else {
+                    w_l = x_l / fmaxf(d[0], 1e-10f);     // poisson_mf_cavi.py:153,157
+                }
+#pragma unroll
+                for (int jj = 0; jj < G; ++jj) {
+                    const float w = __shfl_sync(0xffffffffu, w_l, jj, G);
+                    if constexpr (MODE == 2) {
+                        const float ps = so[jj];
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            sa[v].x = fmaf(w, o[jj][v].x, sa[v].x);  sb[v].x = fmaf(ps, o[jj][v].x, sb[v].x);
+                            sa[v].y = fmaf(w, o[jj][v].y, sa[v].y);  sb[v].y = fmaf(ps, o[jj][v].y, sb[v].y);
+                            sa[v].z = fmaf(w, o[jj][v].z, sa[v].z);  sb[v].z = fmaf(ps, o[jj][v].z, sb[v].z);
+                            sa[v].w = fmaf(w, o[jj][v].w, sa[v].w);  sb[v].w = fmaf(ps, o[jj][v].w, sb[v].w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            sa[v].x = fmaf(w, o[jj][v].x, sa[v].x);  sb[v].x += o[jj][v].x;
+                            sa[v].y = fmaf(w, o[jj][v].y, sa[v].y);  sb[v].y += o[jj][v].y;
+                            sa[v].z = fmaf(w, o[jj][v].z, sa[v].z);  sb[v].z += o[jj][v].z;
+                            sa[v].w = fmaf(w, o[jj][v].w, sa[v].w);  sb[v].w += o[jj][v].w;
+                        }
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int jj = 0; jj < U; ++jj) {
                 const int j = j0 + jj;
@@ -235,6 +295,7 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
             }
         }
     }
+    if constexpr (MODE == 2 && CHUNK_REDUCE) sx = group_sum<G>(sx);   // full mask: the warp is still converged here
     if (!has) return;
     if (pidx < 0) {  // the whole row lives in this segment: finish it here
         gamma_row_update<G, V, MODE>(a, R, gl, group_mask<G>(lane), self, sa, sb, sx, empty);
@@ -325,6 +386,7 @@ __global__ void __launch_bounds__(256) gamma_multi_kernel(const GammaArgs a) {
 static int g_tune_interleave = 0;   // 1 = golden-ratio block interleave of the longest-first order (experiment)
 static int g_tune_group = 0;   // 0 = auto; else forced G for nvec <= 16 (8 or 16)
 static int g_tune_unroll = 0;  // 0 = auto; else forced U
+static int g_tune_chunk_reduce = -1;  // -1 = auto (by gathered-table size), 0 = per-rating dot reduction, 1 = chunk-wide butterfly
 
 static uint32_t gcd_u32(uint32_t x, uint32_t y) {
     while (y) { const uint32_t t = x % y; x = y; y = t; }
@@ -345,9 +407,23 @@ static int launch_gamma(const GammaArgs& a_in, int mode, cudaStream_t s) {
             while (gcd_u32(st, grid) != 1) st += 2;
             a.block_stride = st % grid;
         }
-        if (mode == 2) gamma_pass_kernel<G, V, U, 2><<<grid, 256, 0, s>>>(a);
-        else if (mode == 1) gamma_pass_kernel<G, V, U, 1><<<grid, 256, 0, s>>>(a);
-        else gamma_pass_kernel<G, V, U, 0><<<grid, 256, 0, s>>>(a);
+        // chunk-wide dot reduction needs the whole chunk in registers (U == G); gamma_chunk_reduce=0 keeps the
+        // per-rating reduction for comparison
+        // Measured on C5 (profiles/README.md): with the gathered table around L2 size (user pass, 128 MB) the pass is
+        // bound by instruction issue and gather latency and the chunk-wide reduction is 21 % faster; with a table far
+        // beyond L2 (item pass, 512 MB) the pass is DRAM-bound and prefers the per-rating form, whose accumulation of
+        // early rows overlaps the wait for late ones (12 % faster).  gamma_chunk_reduce: -1 auto, 0 off, 1 on.
+        constexpr bool kCan = U == G;
+        const bool cr = kCan && (g_tune_chunk_reduce < 0 ? a.gather_bytes <= (int64_t)256 << 20 : g_tune_chunk_reduce != 0);
+        if (cr) {
+            if (mode == 2) gamma_pass_kernel<G, V, U, 2, kCan><<<grid, 256, 0, s>>>(a);
+            else if (mode == 1) gamma_pass_kernel<G, V, U, 1, kCan><<<grid, 256, 0, s>>>(a);
+            else gamma_pass_kernel<G, V, U, 0, kCan><<<grid, 256, 0, s>>>(a);
+        } else {
+            if (mode == 2) gamma_pass_kernel<G, V, U, 2, false><<<grid, 256, 0, s>>>(a);
+            else if (mode == 1) gamma_pass_kernel<G, V, U, 1, false><<<grid, 256, 0, s>>>(a);
+            else gamma_pass_kernel<G, V, U, 0, false><<<grid, 256, 0, s>>>(a);
+        }
         PMF_LAUNCH_CHECK();
     }
     if (a.n_multi > 0) {
@@ -365,7 +441,7 @@ static void fill_csr_args(GammaArgs& a, const CsrView& c, int32_t K, int32_t ld)
     a.seg_desc = c.seg_desc;
     a.col = c.col; a.val = c.val; a.multi_row = c.multi_row; a.multi_first = c.multi_first;
     a.n_seg = c.n_seg; a.n_multi = c.n_multi; a.seg_len = c.seg_len; a.row_offset = c.row_offset;
-    a.K = K; a.ld = ld; a.nvec = ld / 4; a.nnz_hint = c.nnz;
+    a.K = K; a.ld = ld; a.nvec = ld / 4; a.nnz_hint = c.nnz; a.gather_bytes = (int64_t)c.n_cols * ld * 4;
     a.scale_oth = nullptr; a.scale_shp = nullptr; a.partial_x = nullptr;
 }
 
@@ -403,6 +479,7 @@ int pmf_tune(const char* key, int value) {
     if (!strcmp(key, "gamma_group")) g_tune_group = value;
     else if (!strcmp(key, "gamma_interleave")) g_tune_interleave = value;
     else if (!strcmp(key, "gamma_unroll")) g_tune_unroll = value;
+    else if (!strcmp(key, "gamma_chunk_reduce")) g_tune_chunk_reduce = value;
     else { set_error("unknown tuning key '%s'", key); return PMF_EINVAL; }
     return PMF_OK;
 }
