@@ -12,7 +12,7 @@ import re
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libpmf_b200.so")
+LIB_PATH = os.environ.get("PMF_B200_LIB") or os.path.join(_PKG, "libpmf_b200.so")   # override: A/B builds of the library
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "pmf_b200.h")
 
 _lock = threading.Lock()

@@ -66,6 +66,51 @@ struct GammaArgs {
 
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
+// Blackwell issues two FP32 multiply-adds per instruction on register pairs (FFMA2 / FADD2): the three 4-wide updates of
+// a rating (dot product, weighted sum, plain sum) take 6 instructions instead of 12.  Each half is an ordinary IEEE
+// operation, so the results are those of the scalar forms (the dot product pairs its terms differently).
+#ifndef PMF_PACKED_FP32
+#define PMF_PACKED_FP32 1
+#endif
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& o) {   // acc += w * o
+#if PMF_PACKED_FP32
+    const float2 ww = make_float2(w, w);
+    const float2 lo = __ffma2_rn(ww, make_float2(o.x, o.y), make_float2(acc.x, acc.y));
+    const float2 hi = __ffma2_rn(ww, make_float2(o.z, o.w), make_float2(acc.z, acc.w));
+    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+#else
+    acc.x = fmaf(w, o.x, acc.x); acc.y = fmaf(w, o.y, acc.y); acc.z = fmaf(w, o.z, acc.z); acc.w = fmaf(w, o.w, acc.w);
+#endif
+}
+__device__ __forceinline__ void add4(float4& acc, const float4& o) {            // acc += o
+#if PMF_PACKED_FP32
+    const float2 lo = __fadd2_rn(make_float2(acc.x, acc.y), make_float2(o.x, o.y));
+    const float2 hi = __fadd2_rn(make_float2(acc.z, acc.w), make_float2(o.z, o.w));
+    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+#else
+    acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+#endif
+}
+template <int V>
+__device__ __forceinline__ float dot4(const float4 (&s)[V], const float4 (&o)[V]) {   // sum_v <s[v], o[v]>
+#if PMF_PACKED_FP32
+    float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        t = __ffma2_rn(make_float2(s[v].x, s[v].y), make_float2(o[v].x, o[v].y), t);
+        t = __ffma2_rn(make_float2(s[v].z, s[v].w), make_float2(o[v].z, o[v].w), t);
+    }
+    return t.x + t.y;
+#else
+    float d = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        d = fmaf(s[v].x, o[v].x, d); d = fmaf(s[v].y, o[v].y, d); d = fmaf(s[v].z, o[v].z, d); d = fmaf(s[v].w, o[v].w, d);
+    }
+    return d;
+#endif
+}
+
 // Sum over the G lanes of a group.  `mask` names the participating lanes: the full warp inside the
 // warp-uniform main loop, only the group's own lanes in the (group-divergent) epilogues.
 template <int G>
@@ -205,17 +250,7 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
                 // weights are handed back with one shuffle per rating.
                 float d[G];
 #pragma unroll
-                for (int jj = 0; jj < G; ++jj) {
-                    float t = 0.f;
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        t = fmaf(self[v].x, o[jj][v].x, t);
-                        t = fmaf(self[v].y, o[jj][v].y, t);
-                        t = fmaf(self[v].z, o[jj][v].z, t);
-                        t = fmaf(self[v].w, o[jj][v].w, t);
-                    }
-                    d[jj] = t;
-                }
+                for (int jj = 0; jj < G; ++jj) d[jj] = dot4<V>(self, o[jj]);
 #pragma unroll
                 for (int h = G / 2; h > 0; h >>= 1) {
                     const bool up = (gl & h) != 0;
@@ -236,63 +271,32 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
 #pragma unroll
                 for (int jj = 0; jj < G; ++jj) {
                     const float w = __shfl_sync(0xffffffffu, w_l, jj, G);
-                    if constexpr (MODE == 2) {
-                        const float ps = so[jj];
 #pragma unroll
-                        for (int v = 0; v < V; ++v) {
-                            sa[v].x = fmaf(w, o[jj][v].x, sa[v].x);  sb[v].x = fmaf(ps, o[jj][v].x, sb[v].x);
-                            sa[v].y = fmaf(w, o[jj][v].y, sa[v].y);  sb[v].y = fmaf(ps, o[jj][v].y, sb[v].y);
-                            sa[v].z = fmaf(w, o[jj][v].z, sa[v].z);  sb[v].z = fmaf(ps, o[jj][v].z, sb[v].z);
-                            sa[v].w = fmaf(w, o[jj][v].w, sa[v].w);  sb[v].w = fmaf(ps, o[jj][v].w, sb[v].w);
-                        }
-                    } else {
-#pragma unroll
-                        for (int v = 0; v < V; ++v) {
-                            sa[v].x = fmaf(w, o[jj][v].x, sa[v].x);  sb[v].x += o[jj][v].x;
-                            sa[v].y = fmaf(w, o[jj][v].y, sa[v].y);  sb[v].y += o[jj][v].y;
-                            sa[v].z = fmaf(w, o[jj][v].z, sa[v].z);  sb[v].z += o[jj][v].z;
-                            sa[v].w = fmaf(w, o[jj][v].w, sa[v].w);  sb[v].w += o[jj][v].w;
-                        }
+                    for (int v = 0; v < V; ++v) {
+                        fma4(sa[v], w, o[jj][v]);
+                        if constexpr (MODE == 2) fma4(sb[v], so[jj], o[jj][v]);
+                        else add4(sb[v], o[jj][v]);
                     }
                 }
-                continue;
-            }
+            } else {
 #pragma unroll
             for (int jj = 0; jj < U; ++jj) {
                 const int j = j0 + jj;
                 const float x = __shfl_sync(0xffffffffu, x_l, j, G);
-                float d = 0.f;
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    d = fmaf(self[v].x, o[jj][v].x, d);
-                    d = fmaf(self[v].y, o[jj][v].y, d);
-                    d = fmaf(self[v].z, o[jj][v].z, d);
-                    d = fmaf(self[v].w, o[jj][v].w, d);
-                }
-                d = group_sum<G>(d);
+                const float d = group_sum<G>(dot4<V>(self, o[jj]));
                 if constexpr (MODE == 2) {
                     // poisson_mf_extended_cavi.py:142 divides by the raw dot product; lanes past the segment end add 0
                     const float w = j < rem ? x / d : 0.f;
-                    const float ps = so[jj];
                     sx += x;
 #pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        sa[v].x = fmaf(w, o[jj][v].x, sa[v].x);  sb[v].x = fmaf(ps, o[jj][v].x, sb[v].x);
-                        sa[v].y = fmaf(w, o[jj][v].y, sa[v].y);  sb[v].y = fmaf(ps, o[jj][v].y, sb[v].y);
-                        sa[v].z = fmaf(w, o[jj][v].z, sa[v].z);  sb[v].z = fmaf(ps, o[jj][v].z, sb[v].z);
-                        sa[v].w = fmaf(w, o[jj][v].w, sa[v].w);  sb[v].w = fmaf(ps, o[jj][v].w, sb[v].w);
-                    }
+                    for (int v = 0; v < V; ++v) { fma4(sa[v], w, o[jj][v]); fma4(sb[v], so[jj], o[jj][v]); }
                     continue;
                 }
                 const float w = x / fmaxf(d, 1e-10f);  // poisson_mf_cavi.py:153,157 (x = 0 past the segment end)
 #pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    sa[v].x = fmaf(w, o[jj][v].x, sa[v].x);  sb[v].x += o[jj][v].x;
-                    sa[v].y = fmaf(w, o[jj][v].y, sa[v].y);  sb[v].y += o[jj][v].y;
-                    sa[v].z = fmaf(w, o[jj][v].z, sa[v].z);  sb[v].z += o[jj][v].z;
-                    sa[v].w = fmaf(w, o[jj][v].w, sa[v].w);  sb[v].w += o[jj][v].w;
-                }
+                for (int v = 0; v < V; ++v) { fma4(sa[v], w, o[jj][v]); add4(sb[v], o[jj][v]); }
             }
+            }   // per-rating reduction
         }
     }
     if constexpr (MODE == 2 && CHUNK_REDUCE) sx = group_sum<G>(sx);   // full mask: the warp is still converged here
