@@ -359,10 +359,10 @@ def main():
     pass_ms = t_user + t_item                                       # includes the NCCL row exchange when N > 1
     achieved = alg_bytes / (pass_ms * 1e-3) / 1e9
     # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the two pass launches of one sweep, from the ncu
-    # --set full capture of this command committed as profiles/r1_gamma_pass_final_ncu_full.csv: user pass
-    # 11.5 + 1.6 GB, item pass 20.3 + 0.4 GB.  Below the algorithmic bytes because the 128 MB item table is half
+    # --set full capture of this command committed as profiles/r1_gamma_pass_final2_ncu_full.csv: user pass
+    # 10.4 + 1.6 GB, item pass 20.1 + 0.4 GB.  Below the algorithmic bytes because the 128 MB item table is half
     # L2-resident.  Only known for the configuration that was captured.
-    traffic = 33.8e9 if (w.name == "c5" and world == 1) else None
+    traffic = 32.5e9 if (w.name == "c5" and world == 1) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_note": "DRAM bytes per sweep (both pass launches), ncu capture in profiles/; "
                 "achieved counts algorithmic bytes per sweep the same way",
