@@ -172,7 +172,7 @@ int pmf_hpf_elbo(const pmf_csr* by_user, int32_t K, int32_t ld, const float* d_E
  * CUDA-core scoring).  d_stats (int32[2], may be NULL): rows that fell back to exact scoring, candidates re-scored.
  * PARITY UNPINNED: the reference has no top-n code; semantics = oracle/pmf_oracle.py::topn. */
 int64_t pmf_topn_workspace_bytes(int64_t batch_rows, int32_t n_items, int32_t K);   /* enough for every mode and n */
-/* Exact requirement of one mode.  tensor_cores: 0 exact CUDA-core scoring; 1 tcgen05, fused (n <= 256 and K <= 208: a
+/* Exact requirement of one mode.  tensor_cores: 0 exact CUDA-core scoring; 1 tcgen05, fused (n <= 256 and K <= 160: a
  * persistent warp-specialised kernel tests every score against a per-row threshold in the MMA epilogue, so the
  * batch x n_items score matrix never reaches HBM and the workspace is ~32 KB per row), unfused otherwise;
  * 2 tcgen05 unfused (score matrix through HBM, 4*n_items bytes per row; kept as the comparison point). */

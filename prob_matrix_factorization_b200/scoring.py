@@ -31,7 +31,7 @@ def top_n(F_user, F_item, n=50, user_rows=None, tensor_cores=True, batch_rows=No
 
     Returns ``(idx int32[B, n], score float32[B, n])`` as NumPy arrays.  ``tensor_cores=True`` scores with
     tcgen05 (bf16 operands) and re-scores a provably sufficient candidate set exactly, so the indices equal
-    the exact path's bit for bit; for n <= 256 and K <= 208 the scores are filtered in the MMA epilogue and
+    the exact path's bit for bit; for n <= 256 and K <= 160 the scores are filtered in the MMA epilogue and
     never written to HBM.  ``tensor_cores="unfused"`` keeps the score matrix in HBM (comparison point),
     ``False`` scores exactly on CUDA cores.  ``batch_rows``: user rows per library call (default 8192 fused,
     1024 otherwise -- the unfused modes need 4*n_items bytes of workspace per row).

@@ -20,7 +20,8 @@ MODES = [False, True, "unfused"]      # exact CUDA cores / tcgen05 fused filter 
 
 @pytest.mark.parametrize("tensor", MODES)
 @pytest.mark.parametrize("B,M,K,n,kind", [(5, 300, 10, 7, "gamma"), (200, 1000, 100, 50, "gamma"), (130, 2500, 64, 50, "normal"),
-                                          (64, 129, 50, 50, "gamma"), (300, 5000, 200, 256, "normal")])
+                                          (64, 129, 50, 50, "gamma"), (300, 5000, 200, 256, "normal"),
+                                          (260, 3000, 160, 100, "normal")])      # K = 160: widest fused shape (2 item stages)
 def test_topn_matches_oracle(tensor, B, M, K, n, kind):
     from prob_matrix_factorization_b200.scoring import top_n
     Fu, Fi = factors(B, M, K, seed=B + M, kind=kind)
