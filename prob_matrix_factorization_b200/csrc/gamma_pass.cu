@@ -27,6 +27,7 @@
 
 namespace pmf {
 
+extern int g_tune_topn_growth;   // topn_fused.cu
 constexpr int kMaxPeers = 7;   // 8 GPUs per NVSwitch domain
 
 struct GammaArgs {
@@ -484,6 +485,7 @@ int pmf_tune(const char* key, int value) {
     else if (!strcmp(key, "gamma_interleave")) g_tune_interleave = value;
     else if (!strcmp(key, "gamma_unroll")) g_tune_unroll = value;
     else if (!strcmp(key, "gamma_chunk_reduce")) g_tune_chunk_reduce = value;
+    else if (!strcmp(key, "topn_growth")) g_tune_topn_growth = value;
     else { set_error("unknown tuning key '%s'", key); return PMF_EINVAL; }
     return PMF_OK;
 }

@@ -444,6 +444,8 @@ __global__ void __launch_bounds__(kRefineThreads) topn_refine_kernel(const Refin
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+int g_tune_topn_growth = 0;
+
 static int64_t pad_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 static int fused_stages(int kp16) {
@@ -542,7 +544,8 @@ int topn_fused_run(const TopnProblem& p, void* workspace, int64_t workspace_byte
 
     PMF_TRY(launch_filter(fa, 0, level0_tiles, 1, smem, s));
     int covered = level0_tiles;
-    const int growth = 256 / p.n < 2 ? 2 : 256 / p.n;     // a level adds ~ n * growth entries per row
+    int growth = 256 / p.n < 2 ? 2 : 256 / p.n;           // a level adds ~ n * growth entries per row
+    if (g_tune_topn_growth >= 1) growth = g_tune_topn_growth;
     ra.dense_input = 1;
     while (covered < tiles) {
         ra.final_level = 0;

@@ -50,6 +50,8 @@ K, n = int(os.environ.get("TOPN_K", 100)), int(os.environ.get("TOPN_N", 50))
 MODES = {"fused": True, "unfused": "unfused", "exact": False}
 modes = os.environ.get("TOPN_MODES", "fused,unfused,exact").split(",")
 reps = int(os.environ.get("TOPN_REPS", 3))
+if os.environ.get("TOPN_GROWTH"):
+    _cabi.call("pmf_tune", b"topn_growth", int(os.environ["TOPN_GROWTH"]))
 rng = np.random.default_rng(0)
 Fu = torch.from_numpy(rng.gamma(0.3, 1.0, (B, K)).astype(np.float32)).cuda()
 Fi = torch.from_numpy(rng.gamma(0.3, 1.0, (M, K)).astype(np.float32)).cuda()
