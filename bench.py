@@ -46,6 +46,26 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries also write there (NCCL prints its version banner to fd 1
+    when a communicator is created), so fd 1 is pointed at stderr for everything but the result line."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _RESULT_OUT
+
+
+def emit(line):
+    out = claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -223,7 +243,7 @@ def run_reference_arm(args):
                                        f"row-length distribution), oracle C port (float64), OpenMP over rows"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -244,6 +264,7 @@ def main():
     ap.add_argument("--exchange", default=None, choices=["p2p", "nccl", "mc"], help="multi-GPU row exchange (default p2p)")
     ap.add_argument("--tune", default="", help="comma list key=value passed to pmf_tune (experiments)")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -410,7 +431,7 @@ def main():
             "gpu_launches": eng.launches_per_sweep * steps, "clocks": clocks}
     if clocks is not None:
         clocks["window"] = "pre-roll + warm-up + timed region (same sweeps), nvidia-smi every 50 ms"
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
