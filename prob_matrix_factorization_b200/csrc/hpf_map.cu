@@ -127,6 +127,32 @@ __global__ void adam_dense_kernel(float* __restrict__ p, const float* __restrict
     p[i] = p[i] - step_size * (mi / denom);                    // param.addcdiv_(exp_avg, denom, value=-step_size)
 }
 
+// The same update on four consecutive elements per thread (128-bit accesses: a quarter of the memory instructions for
+// the 28 bytes per parameter this kernel moves); element-wise arithmetic identical to adam_dense_kernel.
+__global__ void __launch_bounds__(256) adam_dense_vec4_kernel(float4* __restrict__ p, const float4* __restrict__ g,
+                                                              float4* __restrict__ m, float4* __restrict__ v, int64_t n4,
+                                                              float beta1, float beta2, float eps, float step_size,
+                                                              float bc2_sqrt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 g4 = g[i];
+    float4 m4 = m[i], v4 = v[i], p4 = p[i];
+    const float gs[4] = {g4.x, g4.y, g4.z, g4.w};
+    float ms[4] = {m4.x, m4.y, m4.z, m4.w}, vs[4] = {v4.x, v4.y, v4.z, v4.w}, ps[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float mi = ms[k] + (gs[k] - ms[k]) * (1.f - beta1);
+        const float vi = vs[k] * beta2 + (1.f - beta2) * gs[k] * gs[k];
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        ms[k] = mi;
+        vs[k] = vi;
+        ps[k] = ps[k] - step_size * (mi / denom);
+    }
+    m[i] = make_float4(ms[0], ms[1], ms[2], ms[3]);
+    v[i] = make_float4(vs[0], vs[1], vs[2], vs[3]);
+    p[i] = make_float4(ps[0], ps[1], ps[2], ps[3]);
+}
+
 template <typename IdT>
 __global__ void __launch_bounds__(256) hpf_map_predict_kernel(const void* users, const void* items, int64_t n,
                                                               const float* __restrict__ theta,
@@ -317,9 +343,16 @@ int pmf_adam_dense_step(float* d_param, const float* d_grad, float* d_exp_avg, f
                         void* stream) {
     PMF_REQUIRE(n >= 0 && (n == 0 || (d_param && d_grad && d_exp_avg && d_exp_avg_sq)), "bad argument");
     if (n == 0) return PMF_OK;
-    adam_dense_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(d_param, d_grad, d_exp_avg, d_exp_avg_sq, n,
-                                                                                beta1, beta2, eps, step_size,
-                                                                                bias_correction2_sqrt);
+    const uintptr_t align = (uintptr_t)d_param | (uintptr_t)d_grad | (uintptr_t)d_exp_avg | (uintptr_t)d_exp_avg_sq;
+    if (n % 4 == 0 && (align & 15) == 0) {
+        adam_dense_vec4_kernel<<<(unsigned)cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+            (float4*)d_param, (const float4*)d_grad, (float4*)d_exp_avg, (float4*)d_exp_avg_sq, n / 4, beta1, beta2, eps,
+            step_size, bias_correction2_sqrt);
+    } else {
+        adam_dense_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(d_param, d_grad, d_exp_avg, d_exp_avg_sq, n,
+                                                                                    beta1, beta2, eps, step_size,
+                                                                                    bias_correction2_sqrt);
+    }
     PMF_LAUNCH_CHECK();
     return PMF_OK;
 }
