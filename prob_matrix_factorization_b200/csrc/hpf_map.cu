@@ -373,8 +373,6 @@ int pmf_hpf_map_predict(const void* d_users, const void* d_items, int32_t id_byt
 
 static int lazy_state_from(const pmf_lazy_adam* st, LazyState& L) {
     PMF_REQUIRE(st != nullptr, "state is NULL");
-    const float* const* groups[4] = {nullptr, nullptr, nullptr, nullptr};
-    (void)groups;
     float* const P[4] = {st->theta, st->beta, st->xi, st->eta};
     float* const Mo[4] = {st->m_theta, st->m_beta, st->m_xi, st->m_eta};
     float* const Vo[4] = {st->v_theta, st->v_beta, st->v_xi, st->v_eta};
