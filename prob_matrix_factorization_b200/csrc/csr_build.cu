@@ -505,8 +505,16 @@ int pmf_csr_free(pmf_csr* c) {
     if (!c) return PMF_OK;
     void* ptrs[] = {c->seg_desc, c->row_ptr, c->perm, c->col, c->val, c->seg_row, c->seg_start, c->seg_partial, c->seg_order,
                     c->row_seg, c->multi_row, c->multi_first};
-    for (void* p : ptrs)
-        if (p) cudaFree(p);
+    // One device-wide synchronisation (no kernel on any stream can still be reading the list), then stream-ordered frees
+    // that hand the buffers back to the pool without a driver round trip each.
+    cudaDeviceSynchronize();
+    for (void* p : ptrs) {
+        if (!p) continue;
+        if (cudaFreeAsync(p, c->alloc_stream) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(p);
+        }
+    }
     delete c;
     return PMF_OK;
 }
