@@ -15,7 +15,8 @@ import numpy as np
 import pandas as pd
 
 MODEL_DIRS = {"PoissonMFCAVI": "poisson_mf", "HPF_CAVI": "hpf_cavi", "GaussianMFCAVI": "gaussian_mf",
-              "HPF_PyTorch": "hpf_pytorch"}
+              "HPF_PyTorch": "hpf_pytorch",
+              "PoissonMFExtendedCAVI": "poisson_mf_extended"}   # no reference script writes this one; same layout
 
 
 def embeddings_of(model):
