@@ -167,3 +167,17 @@ def test_c_oracle_hpf(golden):
     for k in ("gamma_a_theta", "gamma_b_theta", "gamma_a_beta", "gamma_b_beta", "gamma_b_xi", "gamma_b_eta",
               "E_theta", "E_beta", "E_xi", "E_eta"):
         assert rel_max(st[k], g[k]) < TIGHT, k
+
+
+def test_poisson_ext_scalar_rate_identity(golden):
+    """The kernel never makes the reference's second in-row pass (poisson_mf_extended_cavi.py:160-164): by linearity
+    b_phi = b0 + sum_t psi_t (beta_t . theta_new) = b0 + theta_new . (b_theta - b0).  Checked here on the reference's own
+    outputs, in float64, for every row with observations (both sides)."""
+    g = golden("poisson_ext")
+    b0 = g["b0"]
+    for E, b_vec, b_sc, ids, n in ((g["E_theta"], g["b_theta"], g["b_phi"], g["u"], g["n_users"]),
+                                   (g["E_beta"], g["b_beta"], g["b_psi"], g["i"], g["n_items"])):
+        seen = np.bincount(ids, minlength=n) > 0
+        lhs = b_sc[seen]
+        rhs = b0 + np.sum(E[seen] * (b_vec[seen] - b0), axis=1)
+        assert rel_max(rhs, lhs) < 1e-12
