@@ -261,7 +261,7 @@ def main():
     ap.add_argument("--seg-len", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--exchange", default=None, choices=["p2p", "nccl", "mc"], help="multi-GPU row exchange (default p2p)")
+    ap.add_argument("--exchange", default=None, choices=["nccl", "mc"], help="multi-GPU combine of the item pass (default mc)")
     ap.add_argument("--tune", default="", help="comma list key=value passed to pmf_tune (experiments)")
     args = ap.parse_args()
     claim_stdout()
@@ -340,7 +340,7 @@ def main():
     t_pre = time.perf_counter()
     n_pre = 0
     while True:
-        eng.sweep()
+        eng.sweep(False)
         n_pre += 1
         if n_pre % 4 == 0:
             torch.cuda.synchronize()
@@ -350,17 +350,18 @@ def main():
             if flag.item() > 0:
                 break
     for _ in range(warmup):
-        eng.sweep()
+        eng.sweep(False)
     barrier()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record()
     for s in range(steps):
+        wp = s == steps - 1                       # as in fit(): only the last sweep materialises the Gamma shape/rate tables
         ev[s][0].record()
-        eng.user_pass()
+        eng.user_pass(wp)
         ev[s][1].record()
-        eng.item_pass()
+        eng.item_pass(wp)
         ev[s][2].record()
     stop.record()
     barrier()
@@ -415,18 +416,18 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{w.name}: {w.model} K={w.n_factors}, {w.n_users} users x {w.n_items} items x "
                                    f"{w.nnz} ratings (BASELINE.json configs[{int(w.name[1]) - 1}])",
-                       "sharding": "ratings by nonzero (row-aligned), factors replicated" if world > 1 else "single GPU",
-                       "row_exchange": {"p2p": "fused into the pass kernel: P2P stores to peer replicas over NVLink + "
-                                               "1-element NCCL all-reduce as inter-pass barrier",
-                                        "mc": "fused into the pass kernel: one multimem.st per row slice, replicated to all "
-                                              "GPUs by the NVSwitch (multicast) + signal-pad barrier between passes",
-                                        "nccl": "NCCL all-gather of owned rows after each pass",
-                                        "none": None}[eng.exchange],
+                       "sharding": "ratings by nonzero along nnz-balanced user ranges; E_theta rows live with their owner, E_beta replicated" if world > 1 else "single GPU",
+                       "combine": {"mc": "item pass: per-rank row sums added in the NVSwitch (multimem.ld_reduce) by the row's "
+                                         "owner, Gamma update, new rows replicated with multimem.st; item rows in "
+                                         f"{eng.item_chunks} chunks, combine of a chunk overlaps the pass over the next",
+                                   "nccl": "item pass: NCCL all-reduce of the row sums, every rank updates every row",
+                                   "none": None}[eng.exchange],
+                       "tiles": {"user_pass": len(eng.r.user_tiles), "item_pass": len(eng.r.item_tiles)},
                        "l2": (f"working set {ws_gb:.2f} GB (ratings + factor tables) vs 126 MB L2: "
                               + ("inputs larger than L2, no flush" if ws_gb > 0.5 else
                                  "comparable to L2 -- tables stay L2-resident between sweeps, as they do in a real fit; "
                                  "no flush (a flush would time a cold start no training loop sees)")),
-                       "seg_len": eng.r.by_user.seg_len if eng.r.by_user is not None else None},
+                       "seg_len": eng.r.seg_len},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": eng.launches_per_sweep * steps, "clocks": clocks}
     if clocks is not None:

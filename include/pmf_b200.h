@@ -39,8 +39,13 @@ int pmf_device_count(int* count);      /* fails (PMF_ECUDA) when no CUDA driver/
 int pmf_row_stride(int K);             /* smallest legal `ld` for K factors */
 /* Blocking device->host copy of `bytes` bytes (diagnostics / tests; synchronises the stream). */
 int pmf_copy_to_host(void* h_dst, const void* d_src, int64_t bytes, void* stream);
-/* Kernel-variant selection for experiments ("gamma_group", "gamma_unroll"; 0 = automatic). */
+/* Kernel-variant selection for experiments ("gamma_group", "gamma_unroll"; 0 = automatic).  Process-wide and not
+ * synchronised: set before launching work, never while another thread is inside the library. */
 int pmf_tune(const char* key, int value);
+/* Return the library's cached (freed but retained) device memory of the current device to the driver.  The library
+ * allocates rating lists and scratch from its own stream-ordered pool (it never changes the default pool's settings)
+ * and keeps up to PMF_POOL_KEEP_MB (default 8192) MB across fits.  Synchronises the device. */
+int pmf_trim(void);
 
 /* ---- a1: observation grouping ("CSR build") ----------------------------------------
  * Replaces _build_index_lists (poisson_mf_cavi.py:73-84, hpf_cavi.py:97-107,
@@ -62,6 +67,8 @@ int pmf_csr_build(const int32_t* d_key, const int32_t* d_other, const float* d_v
 /* Copy of rows [row_begin,row_end) as a self-contained structure (row ids stay GLOBAL via
  * pmf_csr_row_offset); used to shard the rating list by nonzero across GPUs. */
 int pmf_csr_slice(const pmf_csr* src, int32_t row_begin, int32_t row_end, void* stream, pmf_csr** out);
+/* Global id of local row 0 (a list built from rebased keys `id - row_offset` of one rank's / one tile's row range). */
+int pmf_csr_set_row_offset(pmf_csr* csr, int32_t row_offset);
 int pmf_csr_free(pmf_csr* csr);
 int64_t pmf_csr_nnz(const pmf_csr* csr);
 int32_t pmf_csr_rows(const pmf_csr* csr);
@@ -77,6 +84,17 @@ int64_t pmf_csr_device_bytes(const pmf_csr* csr);
 /* nnz-balanced, row-aligned partition of the rows into `parts` ranges:
  * h_bounds[parts+1] (host) receives the row boundaries.  Synchronises. */
 int pmf_csr_partition(const pmf_csr* csr, int32_t parts, int32_t* h_bounds);
+
+/* Routing of a (u, i, rating) list to shards / tiles (new; no reference counterpart -- the reference is single-process).
+ * pmf_count_keys: d_counts[k] = number of keys equal to k (int32[n_bins], zeroed by the call); synchronises.
+ * pmf_coo_partition: STABLE partition of the triples by the bucket of u (by_item == 0) or i (by_item != 0), bucket b =
+ * ids in [h_bounds[b], h_bounds[b+1]) (n_buckets <= 256; every id must lie in [h_bounds[0], h_bounds[n_buckets])).
+ * Original order is kept inside a bucket, so grouping a bucket afterwards gives the reference's per-row order.
+ * h_offsets[n_buckets+1] receives the start of each bucket in the outputs.  Synchronises. */
+int pmf_count_keys(const int32_t* d_key, int64_t n, int32_t n_bins, int32_t* d_counts, void* stream);
+int pmf_coo_partition(const int32_t* d_u, const int32_t* d_i, const float* d_x, int64_t n, int32_t by_item,
+                      const int32_t* h_bounds, int32_t n_buckets, int32_t* d_u_out, int32_t* d_i_out, float* d_x_out,
+                      int64_t* h_offsets, void* stream);
 
 /* ---- a3/a4: Gamma-Poisson row pass (Poisson MF and HPF-CAVI) ------------------------
  * Replaces the per-row loops poisson_mf_cavi.py:135-164 / :173-194 (+ E=a/b :167,:197) and
@@ -103,20 +121,34 @@ int pmf_gamma_pass(const pmf_csr* csr, int32_t K, int32_t ld,
                    float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior,
                    void* d_workspace, void* stream);
 
-/* Multi-GPU variant with the row exchange FUSED into the pass: every finished row of
- * E_self (and hyper_mean) is also stored, by the kernel that computed it, into the other ranks' replicas
- * through peer-mapped pointers (NVLink P2P stores), so the transfer overlaps the pass tile by tile and no
- * separate all-gather is needed; callers barrier across ranks between passes.  h_peer_* are HOST arrays of
- * n_peers (<= 7) device pointers obtained from pmf_ipc_open; h_peer_hyper_mean may be NULL (the hyper mean
- * is only read by the rank that owns the row, so replicas can be refreshed once after the last sweep).
- * n_peers == -1: h_peer_E_self[0] is an NVSwitch MULTICAST address of E_self; each finished row is then pushed
- * to every replica with one multimem.st (in-switch replication) instead of one store per peer. */
-int pmf_gamma_pass_p2p(const pmf_csr* csr, int32_t K, int32_t ld,
+/* Tiled / sharded form of the pass (new; the reference is single-process and visits each row's ratings in one go).
+ * The ratings of a pass are split by the id range of the OTHER side into "tiles" -- one pmf_csr per tile -- so that the
+ * part of E_oth a launch gathers from stays resident in the 126 MB L2; on several GPUs every rank additionally holds
+ * only the ratings of its own user range.  The row sums [sum_t (val_t/rate_t) E_oth[col_t] | sum_t E_oth[col_t]]
+ * accumulate across the launches in d_acc[(R - acc_row_base)][2*ld]:
+ *   acc_flags & PMF_ACC_IN   add the sums parked by earlier tiles before using this tile's;
+ *   acc_flags & PMF_ACC_OUT  park the running sums instead of finishing the row.
+ * flags 0 = pmf_gamma_pass; first tile OUT, middle tiles IN|OUT, last tile IN (finishes the rows exactly as
+ * pmf_gamma_pass does) -- or IN|OUT everywhere followed by pmf_gamma_combine (several GPUs).  A row with no rating in
+ * a tile leaves the running sums untouched (IN|OUT), zeroes them (OUT) or finishes from them (IN). */
+#define PMF_ACC_IN 1
+#define PMF_ACC_OUT 2
+int pmf_gamma_pass_acc(const pmf_csr* csr, int32_t K, int32_t ld,
                        const float* d_E_oth, float* d_E_self, float* d_shp, float* d_rte,
                        float shape_prior, float rate_prior, const float* d_rate_prior_vec,
                        float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior,
-                       void* d_workspace, int32_t n_peers, void* const* h_peer_E_self,
-                       void* const* h_peer_hyper_mean, void* stream);
+                       void* d_workspace, float* d_acc, int32_t acc_row_base, int32_t acc_flags, void* stream);
+/* The per-iteration "sufficient statistics combine" of the multi-GPU item pass, fused with the Gamma
+ * update and the replication of the new rows.  For rows [row_begin,row_end) -- the ones this rank owns -- the row sums
+ * are read from d_mc_acc, an NVSwitch MULTICAST alias of every rank's d_acc: one multimem.ld_reduce.add per 16 bytes, the
+ * ranks' partial sums are added inside the switch; the update of pmf_gamma_pass follows; the new row of E_self is
+ * stored locally and, when d_mc_E_self (multicast alias of E_self) is given, to every replica with one multimem.st.
+ * d_mc_acc == NULL: d_acc already holds complete sums (after an NCCL all-reduce; every rank then updates every row).
+ * Callers barrier across ranks before (all partial sums parked) and after (all replicas written). */
+int pmf_gamma_combine(int32_t row_begin, int32_t row_end, int32_t K, int32_t ld, const float* d_acc,
+                      const float* d_mc_acc, int32_t acc_row_base, float* d_E_self, float* d_mc_E_self, float* d_shp,
+                      float* d_rte, float shape_prior, float rate_prior, const float* d_rate_prior_vec,
+                      float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior, void* stream);
 
 /* Extended Poisson MF (poisson_mf_extended_cavi.py:110-164 user side, :169-216 item side):
  * x_ui ~ Poisson(phi_u psi_i theta_u . beta_i).  One pass over the rows of `csr`:
@@ -135,11 +167,6 @@ int pmf_gamma_pass_ext(const pmf_csr* csr, int32_t K, int32_t ld, const float* d
 /* out[r][:] = scale[r] * F[r][:] for rows x ld floats (folds phi / psi into the factor tables so that the extended
  * model's predictions phi_u psi_i theta_u . beta_i go through pmf_predict / pmf_eval_stats). */
 int pmf_scale_rows(const float* d_F, const float* d_scale, int64_t rows, int32_t ld, float* d_out, void* stream);
-/* Peer-mappable device memory (CUDA IPC): allocate + export a 64-byte handle / map a peer's handle. */
-int pmf_ipc_alloc(int64_t bytes, void** d_ptr, void* handle64);
-int pmf_ipc_open(const void* handle64, void** d_ptr);
-int pmf_ipc_close(void* d_ptr);
-int pmf_ipc_free(void* d_ptr);
 
 /* ---- a11: textbook-HPF extras (no reference code exists: docs/Models.tex:583-726 only; PARITY UNPINNED) ----
  * pmf_gamma_geomean: G = exp(psi(shape)) / rate (the geometric-mean table, exp(E log x)), padding columns 0.

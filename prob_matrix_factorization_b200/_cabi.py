@@ -49,6 +49,11 @@ _PROTOTYPES = {
     "pmf_csr_build": (C.c_int, [VP, VP, VP, C.c_int64, C.c_int32, C.c_int32, VP, C.POINTER(VP)]),
     "pmf_csr_slice": (C.c_int, [VP, C.c_int32, C.c_int32, VP, C.POINTER(VP)]),
     "pmf_csr_free": (C.c_int, [VP]),
+    "pmf_csr_set_row_offset": (C.c_int, [VP, C.c_int32]),
+    "pmf_count_keys": (C.c_int, [VP, C.c_int64, C.c_int32, VP, VP]),
+    "pmf_coo_partition": (C.c_int, [VP, VP, VP, C.c_int64, C.c_int32, c_i32p, C.c_int32, VP, VP, VP,
+                                    C.POINTER(C.c_int64), VP]),
+    "pmf_trim": (C.c_int, []),
     "pmf_csr_nnz": (C.c_int64, [VP]),
     "pmf_csr_rows": (C.c_int32, [VP]),
     "pmf_csr_row_offset": (C.c_int32, [VP]),
@@ -64,14 +69,12 @@ _PROTOTYPES = {
     "pmf_gamma_pass_workspace_bytes": (C.c_int64, [VP, C.c_int32]),
     "pmf_gamma_pass": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP, VP, VP, C.c_float, C.c_float, VP,
                                  VP, VP, C.c_float, C.c_float, VP, VP]),
-    "pmf_gamma_pass_p2p": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP, VP, VP, C.c_float, C.c_float, VP,
-                                     VP, VP, C.c_float, C.c_float, VP, C.c_int32, C.POINTER(VP), C.POINTER(VP), VP]),
+    "pmf_gamma_pass_acc": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP, VP, VP, C.c_float, C.c_float, VP,
+                                     VP, VP, C.c_float, C.c_float, VP, VP, C.c_int32, C.c_int32, VP]),
+    "pmf_gamma_combine": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, VP, VP, C.c_int32, VP, VP, VP, VP,
+                                    C.c_float, C.c_float, VP, VP, VP, C.c_float, C.c_float, VP]),
     "pmf_gamma_pass_ext": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP, VP, VP, VP, VP, VP, VP, C.c_float, C.c_float, VP, VP]),
     "pmf_scale_rows": (C.c_int, [VP, VP, C.c_int64, C.c_int32, VP, VP]),
-    "pmf_ipc_alloc": (C.c_int, [C.c_int64, C.POINTER(VP), VP]),
-    "pmf_ipc_open": (C.c_int, [VP, C.POINTER(VP)]),
-    "pmf_ipc_close": (C.c_int, [VP]),
-    "pmf_ipc_free": (C.c_int, [VP]),
     "pmf_gamma_geomean": (C.c_int, [VP, VP, C.c_int64, C.c_int32, C.c_int32, VP, VP]),
     "pmf_gamma_pass_digamma": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP, VP, VP, VP, VP, C.c_float, C.c_float, VP,
                                          VP, VP, C.c_float, C.c_float, VP, VP]),

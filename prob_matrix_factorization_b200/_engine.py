@@ -14,10 +14,11 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .parallel import PeerTable, RowExchange
-from .ratings import DeviceRatings, as_id_array, to_device
+from .parallel import RowExchange, owned_item_ranges
+from .ratings import DeviceRatings, Grouped, as_id_array, to_device
 
 MAX_DEVICE_LABELS = 64
+PMF_ACC_IN, PMF_ACC_OUT = 1, 2     # include/pmf_b200.h
 
 
 class Trace:
@@ -79,18 +80,31 @@ def normalise_ids(ids, n):
 class EvalSet:
     """A (u, i, rating) frame staged on the device for repeated evaluation."""
 
-    def __init__(self, users, items, y, n_users, n_items, device, drop_invalid=False):
+    def __init__(self, users, items, y, n_users, n_items, device, drop_invalid=False, user_range=None):
+        """``user_range=(lo, hi, is_last)`` (multi-GPU fit in progress): keep only the rows whose user this rank owns
+        -- unseen users (id >= n_users) go to the last rank -- and mark the set ``sharded``: its statistics are summed
+        over the ranks, so every rank sees the same numbers (and takes the same early-stopping decision)."""
         users = np.asarray(users)
         items = np.asarray(items)
         y = np.asarray(y, dtype=np.float64)
-        self.n = len(y)
         self.drop_invalid = bool(drop_invalid)
+        self.sharded = user_range is not None
         u32, i32 = normalise_ids(users, n_users), normalise_ids(items, n_items)
+        labels_all = None
+        if self.sharded:
+            if drop_invalid:
+                raise NotImplementedError("sharded evaluation with drop_invalid")
+            labels_all = np.unique(y)                       # labels are those of the WHOLE frame on every rank
+            lo, hi, is_last = user_range
+            uc = np.minimum(u32, n_users)
+            keep = (uc >= lo) & ((uc < hi) | bool(is_last))
+            u32, i32, y = u32[keep], i32[keep], y[keep]
+        self.n = len(y)
         y_for_labels = y
         if drop_invalid:  # gaussian_mf_cavi_bias.py:323-324 filters before np.unique sees the labels
             ok = (u32 < n_users) & (i32 < n_items)
             y_for_labels = y[ok]
-        labels = np.unique(y_for_labels)
+        labels = np.unique(y_for_labels) if labels_all is None else labels_all
         self.labels = labels
         self.on_device = 0 < len(labels) <= MAX_DEVICE_LABELS
         self.y_host = y
@@ -114,6 +128,9 @@ def eval_stats(ev, F_user, F_item, n_users, n_items, K, ld, b_user=None, b_item=
                    ev.n_labels, ev.n, F_user.data_ptr(), n_users, F_item.data_ptr(), n_items, K, ld,
                    _cabi.ptr(b_user), _cabi.ptr(b_item), float(global_mean), int(ev.drop_invalid),
                    ev.out.data_ptr(), _cabi.stream_ptr())
+        if ev.sharded:
+            import torch.distributed as dist
+            dist.all_reduce(ev.out)                          # float64 sums over the ranks' rows: identical everywhere
         out = ev.out.cpu().numpy()
     cnt = out[0]
     res = {"count": cnt, "rmse": float(np.sqrt(out[1] / cnt)) if cnt > 0 else float("nan"),
@@ -121,6 +138,8 @@ def eval_stats(ev, F_user, F_item, n_users, n_items, K, ld, b_user=None, b_item=
     if ev.on_device:
         sae, c = out[4:4 + ev.n_labels], out[4 + ev.n_labels:4 + 2 * ev.n_labels]
         res["macro_mae"] = float(np.mean(sae[c > 0] / c[c > 0])) if (c > 0).any() else float("nan")
+    elif ev.sharded:
+        raise NotImplementedError(f"more than {MAX_DEVICE_LABELS} distinct ratings in a sharded evaluation")
     else:
         # more distinct true values than the fused kernel tracks: reduce predictions per label on host
         pred = predict(ev.u, ev.i, F_user, F_item, n_users, n_items, K, ld, b_user, b_item, global_mean)
@@ -146,36 +165,42 @@ def predict(u_dev, i_dev, F_user, F_item, n_users, n_items, K, ld, b_user=None, 
 
 
 class GammaEngine:
-    """Poisson MF / HPF-CAVI state on one GPU (one shard of the ratings) and its sweep.
+    """Poisson MF / HPF-CAVI state on one GPU (one user-range shard of the ratings) and its sweep.
 
     Sweep order follows SURVEY.md Appendix A: user pass (old E_theta, E_beta[, E_xi]) -> E_theta
     [-> xi] -> item pass (NEW E_theta, old E_beta[, E_eta]) -> E_beta [-> eta]; two dependent
-    SDDMM+reduce passes per iteration.
+    SDDMM+reduce passes per iteration.  Each pass visits its tiles (ratings.py) in turn; on several
+    GPUs the item pass ends with the cross-rank combine of the row sums:
+
+      "mc"   (default) pmf_gamma_combine: multimem.ld_reduce adds the ranks' sums inside the NVSwitch, the owner
+             updates the row and multimem.st replicates it; the item rows are processed in `item_chunks` chunks so
+             that the combine of one chunk (side stream) overlaps the pass over the next;
+      "nccl" unfused baseline: NCCL all-reduce of the sums, every rank updates every row.
     """
 
     def __init__(self, ratings: DeviceRatings, K, user_shape, item_shape, user_rate=None, item_rate=None,
-                 hyper=None, keep_params=True, exchange=None):
+                 hyper=None, keep_params=True, exchange=None, item_chunks=None):
         self.r = ratings
         self.dev = ratings.device
         self.K = int(K)
         self.ld = row_stride(K)
         self.N, self.M = ratings.n_users, ratings.n_items
+        self.world, self.rank = ratings.world, ratings.rank
+        self.user_lo, self.user_hi = ratings.user_lo, ratings.user_hi
         self.user_shape, self.item_shape = float(user_shape), float(item_shape)
         self.user_rate = None if user_rate is None else float(user_rate)
         self.item_rate = None if item_rate is None else float(item_rate)
         # hyper = dict(user_shape=a_xi, user_rate_prior=b', item_shape=a_eta, item_rate_prior=d') for HPF
         self.hyper = hyper
         self.keep_params = keep_params
-        f = lambda rows: torch.zeros((rows, self.ld), dtype=torch.float32, device=self.dev)
-        # multi-GPU row exchange, all fused into the pass kernel except "nccl":
-        #   "mc"   one multimem.st per row slice, replicated by the NVSwitch (default; falls back to "p2p")
-        #   "p2p"  one store per peer into CUDA-IPC mapped replicas
-        #   "nccl" all-gather of owned rows after the pass
+        f = lambda rows, cols=self.ld: torch.zeros((rows, cols), dtype=torch.float32, device=self.dev)
         if exchange is None:
             exchange = os.environ.get("PMF_EXCHANGE", "mc")
-        self.exchange = exchange if ratings.world > 1 else "none"
-        self._peer = {}
+        if exchange not in ("mc", "nccl"):
+            raise ValueError("exchange must be 'mc' or 'nccl'")
+        self.exchange = exchange if self.world > 1 else "none"
         self._symm = {}
+        self._side = None
         if self.exchange == "mc":
             import torch.distributed as dist
             ok, why = 1.0, ""
@@ -187,22 +212,19 @@ class GammaEngine:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # the fallback decision is collective
             if flag.item() < 1.0:
                 import warnings
-                warnings.warn(f"multicast row exchange unavailable ({why or 'on another rank'}); using P2P stores")
+                warnings.warn(f"multicast combine unavailable ({why or 'on another rank'}); using the NCCL all-reduce")
                 self._symm = {}
-                self.exchange = "p2p"
+                self.exchange = "nccl"
+        # E_theta: during a sharded fit only this rank's rows [user_lo, user_hi) are live (nobody else reads them)
+        self.E_theta = f(self.N)
+        n_item_tiles = len(ratings.item_tiles)
         if self.exchange == "mc":
-            self.E_theta, self.E_beta = self._symm["E_theta"][0], self._symm["E_beta"][0]
-        elif self.exchange == "p2p":
-            import torch.distributed as dist
-            # only the factor tables are replicated every pass: E_xi / E_eta are read solely by the rank
-            # that owns the row (rate prior of its own rows), so they are gathered once, at the end
-            for name, shape in (("E_theta", (self.N, self.ld)), ("E_beta", (self.M, self.ld))):
-                self._peer[name] = PeerTable(shape, self.dev)
-            self.E_theta, self.E_beta = self._peer["E_theta"].local, self._peer["E_beta"].local
-            self._token = torch.zeros(1, dtype=torch.float32, device=self.dev)
-            dist.barrier()
+            self.E_beta, self.acc_item = self._symm["E_beta"][0], self._symm["acc_item"][0]
+            self._side = torch.cuda.Stream(device=self.dev)
         else:
-            self.E_theta, self.E_beta = f(self.N), f(self.M)
+            self.E_beta = f(self.M)
+            self.acc_item = f(self.M, 2 * self.ld) if (self.world > 1 or n_item_tiles > 1) else None
+        self.acc_user = f(self.user_hi - self.user_lo, 2 * self.ld) if len(ratings.user_tiles) > 1 else None
         self.shp_theta = f(self.N) if keep_params else None
         self.rte_theta = f(self.N) if keep_params else None
         self.shp_beta = f(self.M) if keep_params else None
@@ -213,154 +235,207 @@ class GammaEngine:
             self.E_xi, self.E_eta = v(self.N), v(self.M)
         else:
             self.rate_xi = self.E_xi = self.rate_eta = self.E_eta = None
-        self.ws_user = ratings.by_user.workspace(self.ld) if ratings.by_user is not None else None
-        self.ws_item = ratings.by_item.workspace(self.ld) if ratings.by_item is not None else None
-        self.xu = RowExchange(ratings.user_bounds) if ratings.world > 1 else None
-        self.xi_ = RowExchange(ratings.item_bounds) if ratings.world > 1 else None
-        self.n_peers = ratings.world - 1 if self.exchange == "p2p" else (-1 if self.exchange == "mc" else 0)
-        self.launches_per_sweep = sum(
-            (1 if g.n_segments > 0 else 0) + (1 if g.n_multi_rows > 0 else 0)
-            for g in (ratings.by_user, ratings.by_item) if g is not None)
+        # item rows in chunks (multicast combine only): chunk c's combine overlaps chunk c+1's pass
+        if item_chunks is None:
+            item_chunks = int(os.environ.get("PMF_ITEM_CHUNKS", 4))
+        self.item_chunks = max(1, min(int(item_chunks), self.M)) if self.exchange == "mc" else 1
+        if self.item_chunks > 1:
+            C_ = self.item_chunks
+            cb = [self.M * c // C_ for c in range(C_ + 1)]
+            self.item_lists = [[g.slice(cb[c], cb[c + 1]) for g in ratings.item_tiles] for c in range(C_)]
+        else:
+            self.item_lists = [list(ratings.item_tiles)]
+        self.owned_items = owned_item_ranges(self.M, self.item_chunks, self.world, self.rank) if self.world > 1 else []
+        ws_bytes = lambda lists: max([g.workspace_bytes(self.ld) for g in lists] + [16])
+        w = lambda nbytes: torch.empty(nbytes // 4, dtype=torch.float32, device=self.dev)
+        self.ws_user = w(ws_bytes(ratings.user_tiles))
+        self.ws_item = w(ws_bytes([g for lst in self.item_lists for g in lst]))
+        self.xu = RowExchange(ratings.user_bounds) if self.world > 1 else None
+        self._item_params_synced = True
+        count = lambda g: (1 if g.n_segments > 0 else 0) + (1 if g.n_multi_rows > 0 else 0)
+        self.launches_per_sweep = (sum(count(g) for g in ratings.user_tiles)
+                                   + sum(count(g) for lst in self.item_lists for g in lst)
+                                   + (self.item_chunks if self.world > 1 else 0))
 
     # -- state upload --------------------------------------------------------------------------
     def load_means(self, E_theta, E_beta, E_xi=None, E_eta=None):
         """Upload the initial expectations (host float64, drawn by NumPy exactly as the reference)."""
-        if self.r.world > 1:
-            # identical host arrays on every rank: 1/world over PCIe each, the rest over NVLink
+        if self.world > 1:
+            # this rank's user rows only; E_beta is replicated: 1/world over PCIe each, the rest over NVLink
             from .parallel import replicate_from_slices
-            for dst, host in ((self.E_theta, E_theta), (self.E_beta, E_beta)):
-                full = replicate_from_slices(np.asarray(host), self.dev, self.r.world, self.r.rank)
-                if full.shape[1] == self.ld and full.dtype == torch.float32:
-                    dst.copy_(full)
-                else:
-                    dst.zero_()
-                    dst[:, :full.shape[1]] = full
+            lo, hi = self.user_lo, self.user_hi
+            if hi > lo:
+                self.E_theta[lo:hi].copy_(pad_table(np.asarray(E_theta)[lo:hi], self.ld, self.dev))
+            full = replicate_from_slices(np.asarray(E_beta), self.dev, self.world, self.rank)
+            if full.shape[1] == self.ld and full.dtype == torch.float32:
+                self.E_beta.copy_(full)
+            else:
+                self.E_beta.zero_()
+                self.E_beta[:, :full.shape[1]] = full
         else:
             self.E_theta.copy_(pad_table(E_theta, self.ld, self.dev))
             self.E_beta.copy_(pad_table(E_beta, self.ld, self.dev))
         if self.hyper is not None:
             self.E_xi.copy_(to_device(np.asarray(E_xi, dtype=np.float32), self.dev))
             self.E_eta.copy_(to_device(np.asarray(E_eta, dtype=np.float32), self.dev))
+        if self.world > 1:
+            torch.cuda.current_stream(self.dev).synchronize()
+            import torch.distributed as dist
+            dist.barrier()                    # every replica of E_beta is in place before any rank's first pass
 
     def download_means(self, out_theta, out_beta, owned_only=False):
         """Copy E_theta / E_beta (first K columns) into caller-provided (pinned) float32 host tensors.
 
-        ``owned_only`` (multi-GPU): copy just this rank's row ranges -- the replicas are identical, so the ranks'
-        owned rows together are the whole result.  Returns the number of bytes copied."""
+        ``owned_only`` (multi-GPU): copy just this rank's user rows and its 1/world share of the (replicated) item
+        rows -- together the ranks' copies are the whole result.  Returns the number of bytes copied."""
         K = self.K
         nbytes = 0
-        for out, tab, bounds in ((out_theta, self.E_theta, self.r.user_bounds), (out_beta, self.E_beta, self.r.item_bounds)):
-            lo, hi = (int(bounds[self.r.rank]), int(bounds[self.r.rank + 1])) if owned_only else (0, tab.shape[0])
+        item_share = (self.M * self.rank // self.world, self.M * (self.rank + 1) // self.world)
+        for out, tab, own in ((out_theta, self.E_theta, (self.user_lo, self.user_hi)), (out_beta, self.E_beta, item_share)):
+            lo, hi = own if owned_only else (0, tab.shape[0])
             src = tab[lo:hi] if self.ld == K else tab[lo:hi, :K]
             out[lo:hi].copy_(src, non_blocking=True)
             nbytes += (hi - lo) * K * 4
         torch.cuda.current_stream(self.dev).synchronize()
         return nbytes
 
+    def eval_range(self):
+        """``user_range`` for EvalSet while a sharded fit is running (None on one GPU)."""
+        if self.world == 1 or self.exchange == "closed":
+            return None
+        return (self.user_lo, self.user_hi, self.rank == self.world - 1)
+
     # -- one pass ------------------------------------------------------------------------------
     def _pass(self, grouped, E_oth, E_self, shp, rte, shape_prior, rate_prior, rate_vec, hyper_rate, hyper_mean,
-              hyper_shape, hyper_rate_prior, ws, peer_E=None):
-        if grouped is None:
-            return
-        _cabi.call("pmf_gamma_pass_p2p", grouped.handle, self.K, self.ld, E_oth.data_ptr(), E_self.data_ptr(),
+              hyper_shape, hyper_rate_prior, ws, acc=None, acc_base=0, flags=0):
+        _cabi.call("pmf_gamma_pass_acc", grouped.handle, self.K, self.ld, E_oth.data_ptr(), E_self.data_ptr(),
                    _cabi.ptr(shp), _cabi.ptr(rte), shape_prior, 0.0 if rate_prior is None else rate_prior,
                    _cabi.ptr(rate_vec), _cabi.ptr(hyper_rate), _cabi.ptr(hyper_mean), hyper_shape,
-                   hyper_rate_prior, _cabi.ptr(ws), self.n_peers if peer_E is not None else 0,
-                   peer_E if peer_E is not None else None, None, _cabi.stream_ptr())
+                   hyper_rate_prior, _cabi.ptr(ws), _cabi.ptr(acc) if flags else None, acc_base, flags,
+                   _cabi.stream_ptr())
+
+    def _combine(self, lo, hi, write_params, multicast):
+        h = self.hyper
+        wp = write_params and self.keep_params
+        _cabi.call("pmf_gamma_combine", lo, hi, self.K, self.ld, self.acc_item.data_ptr(),
+                   self._symm["acc_item"][2] if multicast else None, 0, self.E_beta.data_ptr(),
+                   self._symm["E_beta"][2] if multicast else None,
+                   _cabi.ptr(self.shp_beta if wp else None), _cabi.ptr(self.rte_beta if wp else None),
+                   self.item_shape, 0.0 if self.item_rate is None else self.item_rate, _cabi.ptr(self.E_eta),
+                   _cabi.ptr(self.rate_eta), _cabi.ptr(self.E_eta), h["item_shape"] if h else 0.0,
+                   h["item_rate_prior"] if h else 0.0, _cabi.stream_ptr())
 
     def _setup_multicast(self):
-        """E_theta / E_beta in torch symmetric memory with an NVSwitch multicast alias (plumbing only)."""
+        """E_beta and the item-side row sums in torch symmetric memory with an NVSwitch multicast alias (plumbing)."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         group = dist.group.WORLD
-        for name, rows in (("E_theta", self.N), ("E_beta", self.M)):
-            t = symm_mem.empty((rows, self.ld), dtype=torch.float32, device=self.dev)
+        for name, shape in (("E_beta", (self.M, self.ld)), ("acc_item", (self.M, 2 * self.ld))):
+            t = symm_mem.empty(shape, dtype=torch.float32, device=self.dev)
             hdl = symm_mem.rendezvous(t, group.group_name)
             if not hdl.multicast_ptr:
                 raise RuntimeError("no multicast pointer")
             t.zero_()
-            self._symm[name] = (t, hdl, (C.c_void_p * 1)(hdl.multicast_ptr))
+            self._symm[name] = (t, hdl, int(hdl.multicast_ptr))
         torch.cuda.synchronize(self.dev)
 
     def _rank_barrier(self):
-        """All ranks' pass kernels (and their remote stores into this replica) are complete after this."""
+        """Device-side signal-pad barrier on the current stream: the ranks' work enqueued before it is complete after it."""
+        self._symm["E_beta"][1].barrier(channel=0)
+
+    def user_pass(self, write_params=True):
+        h = self.hyper
+        tiles = self.r.user_tiles
+        wp = write_params and self.keep_params
+        for t, g in enumerate(tiles):
+            last = t == len(tiles) - 1
+            flags = (PMF_ACC_IN if t > 0 else 0) | (0 if last else PMF_ACC_OUT)
+            self._pass(g, self.E_beta, self.E_theta, self.shp_theta if wp else None, self.rte_theta if wp else None,
+                       self.user_shape, self.user_rate, self.E_xi, self.rate_xi, self.E_xi,
+                       h["user_shape"] if h else 0.0, h["user_rate_prior"] if h else 0.0, self.ws_user,
+                       self.acc_user, self.user_lo, flags)
+
+    def item_pass(self, write_params=True):
+        h = self.hyper
+        wp = write_params and self.keep_params
+        self._item_params_synced = self.exchange != "mc"
+        main = torch.cuda.current_stream(self.dev)
+        for c, tiles in enumerate(self.item_lists):
+            for t, g in enumerate(tiles):
+                last = t == len(tiles) - 1 and self.world == 1
+                flags = (PMF_ACC_IN if t > 0 else 0) | (0 if last else PMF_ACC_OUT)
+                self._pass(g, self.E_theta, self.E_beta, self.shp_beta if wp else None, self.rte_beta if wp else None,
+                           self.item_shape, self.item_rate, self.E_eta, self.rate_eta, self.E_eta,
+                           h["item_shape"] if h else 0.0, h["item_rate_prior"] if h else 0.0, self.ws_item,
+                           self.acc_item, 0, flags)
+            if self.exchange == "mc":
+                done = torch.cuda.Event()
+                done.record(main)
+                self._side.wait_event(done)
+                with torch.cuda.stream(self._side):
+                    self._rank_barrier()                        # every rank has parked its sums of chunk c
+                    lo, hi = self.owned_items[c]
+                    self._combine(lo, hi, write_params, multicast=True)
         if self.exchange == "mc":
-            self._symm["E_theta"][1].barrier(channel=0)      # device-side signal-pad barrier on the current stream
-            return
-        import torch.distributed as dist
-        dist.all_reduce(self._token)
+            with torch.cuda.stream(self._side):
+                self._rank_barrier()                            # every rank's new E_beta rows have landed everywhere
+            main.wait_stream(self._side)
+        elif self.exchange == "nccl":
+            import torch.distributed as dist
+            dist.all_reduce(self.acc_item)
+            self._combine(0, self.M, write_params, multicast=False)
 
-    def user_pass(self):
-        h = self.hyper
-        self._pass(self.r.by_user, self.E_beta, self.E_theta, self.shp_theta, self.rte_theta, self.user_shape,
-                   self.user_rate, self.E_xi, self.rate_xi, self.E_xi,
-                   h["user_shape"] if h else 0.0, h["user_rate_prior"] if h else 0.0, self.ws_user,
-                   self._remote("E_theta"))
-        if self.exchange in ("p2p", "mc"):
-            self._rank_barrier()
-        elif self.xu is not None:
-            self.xu.gather(self.E_theta)
-
-    def item_pass(self):
-        h = self.hyper
-        self._pass(self.r.by_item, self.E_theta, self.E_beta, self.shp_beta, self.rte_beta, self.item_shape,
-                   self.item_rate, self.E_eta, self.rate_eta, self.E_eta,
-                   h["item_shape"] if h else 0.0, h["item_rate_prior"] if h else 0.0, self.ws_item,
-                   self._remote("E_beta"))
-        if self.exchange in ("p2p", "mc"):
-            self._rank_barrier()
-        elif self.xi_ is not None:
-            self.xi_.gather(self.E_beta)
-
-    def sweep(self):
+    def sweep(self, write_params=True):
+        """One CAVI iteration.  ``write_params=False`` skips materialising the Gamma shape/rate tables (only the
+        last sweep's are observable; 1.3 GB of writes per sweep at the 100 M-rating config)."""
         with torch.cuda.device(self.dev):
-            self.user_pass()
-            self.item_pass()
-
-    def _remote(self, name):
-        """ctypes array of remote aliases of a table for pmf_gamma_pass_p2p (peers, or the multicast address)."""
-        if self.exchange == "p2p":
-            return self._peer[name].peer_array
-        if self.exchange == "mc":
-            return self._symm[name][2]
-        return None
+            self.user_pass(write_params)
+            self.item_pass(write_params)
 
     def close(self):
-        """Unmap / free peer-shared tables (multi-GPU p2p exchange).  Call on every rank."""
+        """Release the symmetric-memory tables (multi-GPU): state becomes ordinary device tensors.  Collective."""
         if self._symm:
             import torch.distributed as dist
             torch.cuda.synchronize(self.dev)
             dist.barrier()
-            for k, (t, hdl, arr) in self._symm.items():
-                setattr(self, k, t.clone())
+            self.E_beta = self._symm["E_beta"][0].clone()
+            self.acc_item = None
             self._symm = {}
-            self.exchange = "closed"
-            self.n_peers = 0
-        if self._peer:
-            import torch.distributed as dist
-            keep = {k: getattr(self, k).clone() for k in self._peer}     # state stays readable after close
             torch.cuda.synchronize(self.dev)
             dist.barrier()
-            for t in self._peer.values():
-                t.close()
-            self._peer = {}
-            for k, v in keep.items():
-                setattr(self, k, v)
+        if self.exchange != "none":
             self.exchange = "closed"
-            self.n_peers = 0
+
+    def _sync_item_params(self):
+        """Multicast combine: shape/rate/hyper rows of an item are written by its owner only -> make them complete
+        everywhere (the non-owned rows are zeroed and the tables summed over the ranks)."""
+        if self._item_params_synced or self.exchange != "mc":
+            return
+        import torch.distributed as dist
+        mask = torch.zeros(self.M, dtype=torch.bool, device=self.dev)
+        for lo, hi in self.owned_items:
+            mask[lo:hi] = True
+        tabs = [t for t in ((self.rate_eta, self.E_eta) if self.hyper else ()) if t is not None]
+        if self.keep_params:
+            tabs += [self.shp_beta, self.rte_beta]
+        for t in tabs:
+            t[~mask] = 0
+            dist.all_reduce(t)
+        self._item_params_synced = True
 
     def sync_params(self):
-        """Multi-GPU: make the Gamma shape/rate tables (only needed as outputs) complete on every rank."""
-        if self.xu is None:
+        """Multi-GPU: make every table complete on every rank (end of fit: E_theta rows and the Gamma parameters live
+        with their owners only while the sweeps run)."""
+        if self.xu is None or self.exchange == "closed":
             return
+        self.xu.gather(self.E_theta)
         if self.hyper:
             self.xu.gather(self.rate_xi, self.E_xi)
-            self.xi_.gather(self.rate_eta, self.E_eta)
         if self.keep_params:
             self.xu.gather(self.shp_theta, self.rte_theta)
-            self.xi_.gather(self.shp_beta, self.rte_beta)
+        self._sync_item_params()
 
-    # -- a11 extras (single GPU; parity unpinned) ------------------------------------------------
+    # -- a11 extras (parity unpinned) ----------------------------------------------------------------
     def load_params(self, shp_theta, rte_theta, shp_beta, rte_beta, rate_xi, rate_eta):
         """Upload Gamma shape/rate tables (needed before the first sweep by the digamma pass and the ELBO)."""
         for name, host in (("shp_theta", shp_theta), ("rte_theta", rte_theta), ("shp_beta", shp_beta), ("rte_beta", rte_beta)):
@@ -380,9 +455,9 @@ class GammaEngine:
         return self.G_theta, self.G_beta
 
     def sweep_digamma(self):
-        """One sweep with the multinomial (digamma) allocation of docs/Models.tex:652-664."""
-        if self.r.world > 1:
-            raise NotImplementedError("digamma allocation is single-GPU in this round")
+        """One sweep with the multinomial (digamma) allocation of docs/Models.tex:652-664 (single GPU, untiled)."""
+        if self.world > 1:
+            raise NotImplementedError("digamma allocation is single-GPU")
         h = self.hyper
         with torch.cuda.device(self.dev):
             for grouped, G_oth, E_oth, G_self, E_self, shp, rte, shape, rate_vec, hr, hs, hp, ws in (
@@ -395,19 +470,36 @@ class GammaEngine:
                            rate_vec.data_ptr(), hr.data_ptr(), rate_vec.data_ptr(), hs, hp, _cabi.ptr(ws), _cabi.stream_ptr())
 
     def elbo(self, cfg, refresh_geomean=True):
-        """Observed-only HPF ELBO and its six components (pmf_hpf_elbo); one D2H of 6 doubles."""
-        if self.r.world > 1:
-            raise NotImplementedError("ELBO is single-GPU in this round")
+        """Observed-only HPF ELBO and its six components (pmf_hpf_elbo); one D2H of 6 doubles.
+
+        Several GPUs: each rank adds the likelihood of its own ratings, the prior/entropy terms of its own users and of
+        a 1/world share of the items; the six sums are all-reduced (item-side parameters are completed first)."""
+        sharded = self.world > 1 and self.exchange != "closed"
+        if sharded:
+            self._sync_item_params()
         if refresh_geomean or getattr(self, "G_theta", None) is None:
             self.geomean_tables()
-        out = torch.zeros(6, dtype=torch.float64, device=self.dev)
+        tiles = self.r.user_tiles
+        if not tiles:       # a rank without users still owes the row terms of its share of the items
+            z = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            self._empty_list = Grouped.build(z[:0], z[:0], z[:0].float(), 1, 8)
+            tiles = [self._empty_list]
+        out = torch.zeros((len(tiles), 6), dtype=torch.float64, device=self.dev)
+        u_rng = (self.user_lo, self.user_hi) if sharded else (0, self.N)
+        i_rng = (self.M * self.rank // self.world, self.M * (self.rank + 1) // self.world) if sharded else (0, self.M)
         with torch.cuda.device(self.dev):
-            _cabi.call("pmf_hpf_elbo", self.r.by_user.handle, self.K, self.ld, self.E_theta.data_ptr(), self.E_beta.data_ptr(),
-                       self.G_theta.data_ptr(), self.G_beta.data_ptr(), self.shp_theta.data_ptr(), self.rte_theta.data_ptr(),
-                       self.shp_beta.data_ptr(), self.rte_beta.data_ptr(), self.rate_xi.data_ptr(), self.rate_eta.data_ptr(),
-                       0, self.N, 0, self.M, cfg.a, cfg.a_prime, cfg.b_prime, cfg.c, cfg.c_prime, cfg.d_prime,
-                       out.data_ptr(), _cabi.stream_ptr())
-        parts = out.cpu().numpy()
+            for t, g in enumerate(tiles):
+                ur, ir = (u_rng, i_rng) if t == 0 else ((0, 0), (0, 0))     # row terms once, likelihood per tile
+                _cabi.call("pmf_hpf_elbo", g.handle, self.K, self.ld, self.E_theta.data_ptr(), self.E_beta.data_ptr(),
+                           self.G_theta.data_ptr(), self.G_beta.data_ptr(), self.shp_theta.data_ptr(), self.rte_theta.data_ptr(),
+                           self.shp_beta.data_ptr(), self.rte_beta.data_ptr(), self.rate_xi.data_ptr(), self.rate_eta.data_ptr(),
+                           ur[0], ur[1], ir[0], ir[1], cfg.a, cfg.a_prime, cfg.b_prime, cfg.c, cfg.c_prime, cfg.d_prime,
+                           out[t].data_ptr(), _cabi.stream_ptr())
+        parts_d = out.sum(0)
+        if sharded:
+            import torch.distributed as dist
+            dist.all_reduce(parts_d)
+        parts = parts_d.cpu().numpy()
         return float(parts.sum()), parts
 
     # -- accounting ----------------------------------------------------------------------------

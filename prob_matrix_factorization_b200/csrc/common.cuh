@@ -40,12 +40,16 @@ void set_error(const char* fmt, ...);
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Stream-ordered allocation from the LIBRARY's own memory pool of the current device (csr_build.cu): a bounded release
+// threshold keeps a re-fit's buffers cached without touching the process-wide default pool (pmf_trim() empties it).
+cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t s);
+
 // Stream-ordered scratch allocation (freed on the same stream).
 template <typename T>
 inline int alloc_async(T** p, int64_t count, cudaStream_t s) {
     *p = nullptr;
     if (count <= 0) count = 1;
-    PMF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(p), static_cast<size_t>(count) * sizeof(T), s));
+    PMF_CUDA(pool_alloc(reinterpret_cast<void**>(p), static_cast<size_t>(count) * sizeof(T), s));
     return PMF_OK;
 }
 template <typename T>
@@ -68,6 +72,7 @@ struct CsrView {
     // observation, partial-sum slot or -1} -- what a lane group needs to start, in ONE load instead of a chain of three
     const int4* seg_desc;
     int32_t n_cols;   // 1 + largest id of the other side in `col` (extent of the gathered table that can be touched)
+    int32_t col_lo;   // smallest id of the other side in `col`
 };
 CsrView csr_view(const pmf_csr* c);
 

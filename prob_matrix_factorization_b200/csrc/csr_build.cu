@@ -9,6 +9,9 @@
 // are computed with warp match + shared-memory counters, no global atomics.
 #include <stdarg.h>
 
+#include <stdlib.h>
+
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -258,9 +261,53 @@ __global__ void check_keys_kernel(const int32_t* __restrict__ key, const int32_t
         oth = other[p];
         if (key[p] < 0 || key[p] >= n_rows || oth < 0) atomicOr(bad, 1);
     }
-    // bad[1] = largest id of the other side: how many rows of the other side's table the passes can touch
+    // bad[1] / bad[2] = largest / smallest id of the other side: the span of the other side's table the passes can touch
     const int wmax = __reduce_max_sync(0xffffffffu, oth);
-    if ((threadIdx.x & 31) == 0 && wmax >= 0) atomicMax(bad + 1, wmax);
+    const int wmin = __reduce_min_sync(0xffffffffu, oth < 0 ? INT32_MAX : oth);
+    if ((threadIdx.x & 31) == 0 && wmax >= 0) {
+        atomicMax(bad + 1, wmax);
+        atomicMin(bad + 2, wmin);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// routing helpers for sharded / tiled rating lists
+// ------------------------------------------------------------------------------------------
+__global__ void count_keys_kernel(const int32_t* __restrict__ key, int64_t n, int32_t n_bins, int32_t* __restrict__ counts,
+                                  int32_t* __restrict__ bad) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int32_t k = key[p];
+    if (k < 0 || k >= n_bins) { atomicOr(bad, 1); return; }
+    atomicAdd(counts + k, 1);
+}
+
+// bucket[p] = b with bounds[b] <= key[p] < bounds[b+1]  (bounds ascending, bounds[0] <= every key < bounds[nb])
+__global__ void bucket_kernel(const int32_t* __restrict__ key, int64_t n, const int32_t* __restrict__ bounds, int32_t nb,
+                              int32_t* __restrict__ bucket) {
+    __shared__ int32_t sb[257];
+    for (int t = threadIdx.x; t <= nb; t += blockDim.x) sb[t] = bounds[t];
+    __syncthreads();
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int32_t k = key[p];
+    int lo = 0, hi = nb;   // invariant: sb[lo] <= k < sb[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (sb[mid] <= k) lo = mid; else hi = mid;
+    }
+    bucket[p] = lo;
+}
+
+__global__ void gather3_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ a, const int32_t* __restrict__ b,
+                               const float* __restrict__ x, int64_t n, int32_t* __restrict__ a_out, int32_t* __restrict__ b_out,
+                               float* __restrict__ x_out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int32_t t = perm[p];
+    a_out[p] = a[t];
+    b_out[p] = b[t];
+    x_out[p] = x[t];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -331,6 +378,7 @@ struct pmf_csr {
     int64_t nnz = 0;
     int32_t n_rows = 0, row_offset = 0, seg_len = 0;
     int32_t n_cols = 0;            // 1 + largest id of the other side seen in `col`
+    int32_t col_lo = 0;            // smallest id of the other side seen in `col`
     int32_t n_seg = 0, n_multi = 0, n_partial = 0;
     int32_t *row_ptr = nullptr, *perm = nullptr, *col = nullptr;
     float* val = nullptr;
@@ -343,27 +391,53 @@ struct pmf_csr {
     int64_t bytes = 0;
 };
 
-// The rating list's buffers come from the device's stream-ordered memory pool with the release threshold lifted, so a
-// model that is fitted again (tuning loops fit dozens of times; bench.py's timed fit follows an untimed one) gets the
-// previous fit's memory back from the pool instead of paying the driver for ~30 fresh allocations -- on a fresh box
-// those cudaMalloc / cudaFree calls were measured at up to 1 s per fit of the 100 M-rating config.
-static void keep_pool_memory() {
-    static bool done = false;
-    if (done) return;
+// The rating list's buffers (and the library's scratch) come from a LIBRARY-OWNED stream-ordered memory pool, one per
+// device, so a model that is fitted again (tuning loops fit dozens of times; bench.py's timed fit follows an untimed one)
+// gets the previous fit's memory back without paying the driver for ~30 fresh allocations -- on a fresh box those
+// cudaMalloc / cudaFree calls were measured at up to 1 s per fit of the 100 M-rating config.  The pool keeps at most
+// PMF_POOL_KEEP_MB (default 8192) MB of freed memory; the process-wide default pool is never modified, and pmf_trim()
+// returns everything that is not in use to the driver (for callers that go on to allocate through other allocators).
+static std::mutex g_pool_mutex;
+static cudaMemPool_t g_pools[64] = {};
+static bool g_pool_failed[64] = {};
+
+static cudaMemPool_t library_pool() {
     int dev = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t threshold = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_pools[dev] || g_pool_failed[dev]) return g_pools[dev];
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+        cudaGetLastError();   // the pool is an optimisation: fall back to the default pool
+        g_pool_failed[dev] = true;
+        return nullptr;
     }
-    cudaGetLastError();   // the pool is an optimisation: never fail a build over it
-    done = true;
+    uint64_t keep_mb = 8192;
+    if (const char* e = getenv("PMF_POOL_KEEP_MB")) keep_mb = strtoull(e, nullptr, 10);
+    uint64_t threshold = keep_mb << 20;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    cudaGetLastError();
+    g_pools[dev] = pool;
+    return pool;
+}
+
+cudaError_t pmf::pool_alloc(void** p, size_t bytes, cudaStream_t s) {
+    if (cudaMemPool_t pool = library_pool()) {
+        const cudaError_t e = cudaMallocFromPoolAsync(p, bytes, pool, s);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError();
+    }
+    return cudaMallocAsync(p, bytes, s);
 }
 
 static int dev_alloc(void** p, int64_t bytes, pmf_csr* c) {
     if (bytes <= 0) bytes = 4;
-    keep_pool_memory();
-    cudaError_t e = cudaMallocAsync(p, (size_t)bytes, c->alloc_stream);
+    cudaError_t e = pool_alloc(p, (size_t)bytes, c->alloc_stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
         e = cudaMalloc(p, (size_t)bytes);   // e.g. a pool that cannot grow: fall back to a plain allocation
@@ -464,38 +538,9 @@ int pmf_copy_to_host(void* h_dst, const void* d_src, int64_t bytes, void* stream
     return PMF_OK;
 }
 
-// ---- peer-mapped device memory (CUDA IPC) for the fused row exchange -----------------------------------
-int pmf_ipc_alloc(int64_t bytes, void** d_ptr, void* handle64) {
-    PMF_REQUIRE(bytes > 0 && d_ptr && handle64, "bad argument");
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    PMF_CUDA(cudaMalloc(d_ptr, (size_t)bytes));
-    cudaIpcMemHandle_t h;
-    cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
-    if (e != cudaSuccess) {
-        cudaFree(*d_ptr);
-        *d_ptr = nullptr;
-        set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
-        return PMF_ECUDA;
-    }
-    memcpy(handle64, &h, 64);
-    return PMF_OK;
-}
-
-int pmf_ipc_open(const void* handle64, void** d_ptr) {
-    PMF_REQUIRE(handle64 && d_ptr, "bad argument");
-    cudaIpcMemHandle_t h;
-    memcpy(&h, handle64, 64);
-    PMF_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
-    return PMF_OK;
-}
-
-int pmf_ipc_close(void* d_ptr) {
-    if (d_ptr) PMF_CUDA(cudaIpcCloseMemHandle(d_ptr));
-    return PMF_OK;
-}
-
-int pmf_ipc_free(void* d_ptr) {
-    if (d_ptr) PMF_CUDA(cudaFree(d_ptr));
+int pmf_trim(void) {
+    PMF_CUDA(cudaDeviceSynchronize());
+    if (cudaMemPool_t pool = library_pool()) PMF_CUDA(cudaMemPoolTrimTo(pool, 0));
     return PMF_OK;
 }
 
@@ -548,16 +593,17 @@ int pmf_csr_build(const int32_t* d_key, const int32_t* d_other, const float* d_v
     } else {
         auto body = [&]() -> int {
             int32_t* bad = nullptr;
-            PMF_TRY(alloc_async(&bad, 2, s));
-            PMF_CUDA(cudaMemsetAsync(bad, 0, 8, s));
+            PMF_TRY(alloc_async(&bad, 3, s));
+            int32_t h_bad[3] = {0, 0, INT32_MAX};
+            PMF_CUDA(cudaMemcpyAsync(bad, h_bad, 12, cudaMemcpyHostToDevice, s));
             check_keys_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(d_key, d_other, nnz, n_rows, bad);
             PMF_LAUNCH_CHECK();
-            int32_t h_bad[2] = {0, 0};
-            PMF_CUDA(cudaMemcpyAsync(h_bad, bad, 8, cudaMemcpyDeviceToHost, s));
+            PMF_CUDA(cudaMemcpyAsync(h_bad, bad, 12, cudaMemcpyDeviceToHost, s));
             PMF_CUDA(cudaStreamSynchronize(s));
             free_async(bad, s);
             PMF_REQUIRE(h_bad[0] == 0, "ids out of range: keys must lie in [0, %d), other ids must be >= 0", n_rows);
             c->n_cols = h_bad[1] + 1;
+            c->col_lo = h_bad[2] <= h_bad[1] ? h_bad[2] : 0;
 
             int32_t* k0 = nullptr;
             PMF_TRY(alloc_async(&k0, nnz, s));
@@ -594,6 +640,7 @@ int pmf_csr_slice(const pmf_csr* src, int32_t row_begin, int32_t row_end, void* 
     c->row_offset = src->row_offset + row_begin;
     c->seg_len = src->seg_len;
     c->n_cols = src->n_cols;
+    c->col_lo = src->col_lo;
     auto body = [&]() -> int {
         PMF_TRY(dev_alloc((void**)&c->row_ptr, ((int64_t)c->n_rows + 1) * 4, c));
         PMF_TRY(dev_alloc((void**)&c->perm, c->nnz * 4, c));
@@ -615,6 +662,63 @@ int pmf_csr_slice(const pmf_csr* src, int32_t row_begin, int32_t row_end, void* 
         return st;
     }
     *out = c;
+    return PMF_OK;
+}
+
+int pmf_csr_set_row_offset(pmf_csr* c, int32_t row_offset) {
+    PMF_REQUIRE(c != nullptr && row_offset >= 0, "bad argument");
+    c->row_offset = row_offset;
+    return PMF_OK;
+}
+
+int pmf_count_keys(const int32_t* d_key, int64_t n, int32_t n_bins, int32_t* d_counts, void* stream) {
+    PMF_REQUIRE(n >= 0 && n_bins > 0 && d_counts && (n == 0 || d_key), "bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    PMF_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)n_bins * 4, s));
+    if (n == 0) return PMF_OK;
+    int32_t* bad = nullptr;
+    PMF_TRY(alloc_async(&bad, 1, s));
+    PMF_CUDA(cudaMemsetAsync(bad, 0, 4, s));
+    count_keys_kernel<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(d_key, n, n_bins, d_counts, bad);
+    PMF_LAUNCH_CHECK();
+    int32_t h_bad = 0;
+    PMF_CUDA(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, s));
+    PMF_CUDA(cudaStreamSynchronize(s));
+    free_async(bad, s);
+    PMF_REQUIRE(h_bad == 0, "ids out of range: keys must lie in [0, %d)", n_bins);
+    return PMF_OK;
+}
+
+int pmf_coo_partition(const int32_t* d_u, const int32_t* d_i, const float* d_x, int64_t n, int32_t by_item,
+                      const int32_t* h_bounds, int32_t n_buckets, int32_t* d_u_out, int32_t* d_i_out, float* d_x_out,
+                      int64_t* h_offsets, void* stream) {
+    PMF_REQUIRE(n >= 0 && n < (int64_t)INT32_MAX && h_bounds && h_offsets && n_buckets >= 1 && n_buckets <= 256,
+                "bad argument (n=%lld, n_buckets=%d)", (long long)n, n_buckets);
+    PMF_REQUIRE(n == 0 || (d_u && d_i && d_x && d_u_out && d_i_out && d_x_out), "NULL array with n > 0");
+    for (int b = 0; b < n_buckets; ++b) PMF_REQUIRE(h_bounds[b] <= h_bounds[b + 1], "bounds must ascend");
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int b = 0; b <= n_buckets; ++b) h_offsets[b] = 0;
+    if (n == 0) return PMF_OK;
+    int32_t *bounds = nullptr, *bucket = nullptr, *sorted = nullptr, *perm = nullptr, *offs = nullptr;
+    PMF_TRY(alloc_async(&bounds, n_buckets + 1, s));
+    PMF_TRY(alloc_async(&bucket, n, s));
+    PMF_TRY(alloc_async(&sorted, n, s));
+    PMF_TRY(alloc_async(&perm, n, s));
+    PMF_TRY(alloc_async(&offs, n_buckets + 1, s));
+    PMF_CUDA(cudaMemcpyAsync(bounds, h_bounds, (size_t)(n_buckets + 1) * 4, cudaMemcpyHostToDevice, s));
+    const unsigned grid = (unsigned)cdiv(n, 256);
+    bucket_kernel<<<grid, 256, 0, s>>>(by_item ? d_i : d_u, n, bounds, n_buckets, bucket);
+    PMF_LAUNCH_CHECK();
+    PMF_TRY(stable_sort_by_key(bucket, n, 8, sorted, perm, s));
+    row_ptr_kernel<<<grid, 256, 0, s>>>(sorted, n, n_buckets, offs);
+    PMF_LAUNCH_CHECK();
+    gather3_kernel<<<grid, 256, 0, s>>>(perm, d_u, d_i, d_x, n, d_u_out, d_i_out, d_x_out);
+    PMF_LAUNCH_CHECK();
+    std::vector<int32_t> h((size_t)n_buckets + 1);
+    PMF_CUDA(cudaMemcpyAsync(h.data(), offs, h.size() * 4, cudaMemcpyDeviceToHost, s));
+    PMF_CUDA(cudaStreamSynchronize(s));
+    for (int b = 0; b <= n_buckets; ++b) h_offsets[b] = h[b];
+    free_async(bounds, s); free_async(bucket, s); free_async(sorted, s); free_async(perm, s); free_async(offs, s);
     return PMF_OK;
 }
 
@@ -656,6 +760,6 @@ namespace pmf {
 CsrView csr_view(const pmf_csr* c) {
     return CsrView{c->nnz, c->n_rows, c->row_offset, c->seg_len, c->n_seg, c->n_multi, c->n_partial, c->row_ptr,
                    c->col, c->val, c->seg_row, c->seg_start, c->seg_partial, c->seg_order, c->row_seg,
-                   c->multi_row, c->multi_first, c->seg_desc, c->n_cols};
+                   c->multi_row, c->multi_first, c->seg_desc, c->n_cols, c->col_lo};
 }
 }  // namespace pmf

@@ -28,7 +28,6 @@
 namespace pmf {
 
 extern int g_tune_topn_growth;   // topn_fused.cu
-constexpr int kMaxPeers = 7;   // 8 GPUs per NVSwitch domain
 
 struct GammaArgs {
     const int4* seg_desc;   // segments in processing order: {row, start, end, partial slot or -1}
@@ -53,16 +52,16 @@ struct GammaArgs {
     const float* scale_oth;
     float* scale_shp;
     float* partial_x;
-    // fused row exchange (multi-GPU): the other ranks' replicas of E_self / hyper_mean, mapped over NVLink.
-    // Every finished row is stored to all replicas by the same kernel that computed it.
     // block -> chunk of the longest-first segment list: chunk = (blockIdx.x * block_stride) % gridDim.x with
-    // gcd(block_stride, gridDim.x) = 1.  stride 1 = longest first; a large stride interleaves long and short
-    // segments over the launch so that row completions (= P2P row stores) are spread over the whole kernel.
+    // gcd(block_stride, gridDim.x) = 1.  stride 1 = longest first.
     uint32_t block_stride;
-    int32_t n_peers;
+    // Tiled passes (the gathered table is visited one L2-sized row range -- "tile" -- at a time, and, on several GPUs,
+    // one user range per GPU): the row sums [sum (x/rate) E_oth | sum E_oth] accumulate across the tiles in
+    // acc[(R - acc_row_base)][2*ld].  acc_in: add the sums accumulated so far; acc_out: store the running sums instead of
+    // finishing the row (the last tile -- or, across GPUs, gamma_combine_kernel -- applies the Gamma update).
+    float* acc;
+    int32_t acc_in, acc_out, acc_row_base;
     float* mc_E;   // NVSwitch multicast alias of E_self (all replicas at once, multimem.st) or NULL
-    float* peer_E[kMaxPeers];
-    float* peer_hyper_mean[kMaxPeers];
 };
 
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -157,8 +156,6 @@ __device__ __forceinline__ void gamma_row_update(const GammaArgs& a, int R, int 
                 if (empty) continue;   // no observations: prior shape/rate, expectations untouched (:112-118)
             }
             *reinterpret_cast<float4*>(a.E_self + rowoff + k0) = e;
-            for (int pr = 0; pr < a.n_peers; ++pr)   // P2P stores: 16*G contiguous bytes per group and peer
-                *reinterpret_cast<float4*>(a.peer_E[pr] + rowoff + k0) = e;
             if (a.mc_E)   // one store, replicated to every GPU of the multicast group by the NVSwitch
                 asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
                              ::"l"(a.mc_E + rowoff + k0), "f"(e.x), "f"(e.y), "f"(e.z), "f"(e.w) : "memory");
@@ -181,11 +178,46 @@ __device__ __forceinline__ void gamma_row_update(const GammaArgs& a, int R, int 
             const float hr = a.hyper_rate_prior + esum;   // hpf_cavi.py:158 / :192
             const float hm = a.hyper_shape / hr;          // hpf_cavi.py:94-95
             a.hyper_rate[R] = hr;
-            a.hyper_mean[R] = hm;
-            if (a.peer_hyper_mean[0])   // optional: the hyper mean is only read by the row's owner
-                for (int pr = 0; pr < a.n_peers; ++pr) a.peer_hyper_mean[pr][R] = hm;
+            a.hyper_mean[R] = hm;   // only ever read by the row's owner: not replicated
         }
     }
+}
+
+// A row's sums over the current tile are complete (held by the G lanes of a group): fold them into the sums of the
+// earlier tiles and either park the running sums (acc_out) or finish the row.
+template <int G, int V, int MODE>
+__device__ __forceinline__ void finish_row(const GammaArgs& a, int R, int gl, unsigned gmask, const float4 (&self)[V],
+                                           float4 (&sa)[V], float4 (&sb)[V], float sx, bool empty) {
+    if constexpr (MODE != 2) {
+        if (a.acc) {
+            if (a.acc_in && a.acc_out && empty) return;   // nothing of this row in this tile: running sums unchanged
+            float* pr = a.acc + (size_t)(R - a.acc_row_base) * 2 * a.ld;
+            if (a.acc_in) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const int idx = gl + v * G;
+                    if (idx < a.nvec) {
+                        const float4 pa = *reinterpret_cast<const float4*>(pr + idx * 4);
+                        const float4 pb = *reinterpret_cast<const float4*>(pr + a.ld + idx * 4);
+                        sa[v].x = pa.x + sa[v].x; sa[v].y = pa.y + sa[v].y; sa[v].z = pa.z + sa[v].z; sa[v].w = pa.w + sa[v].w;
+                        sb[v].x = pb.x + sb[v].x; sb[v].y = pb.y + sb[v].y; sb[v].z = pb.z + sb[v].z; sb[v].w = pb.w + sb[v].w;
+                    }
+                }
+            }
+            if (a.acc_out) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const int idx = gl + v * G;
+                    if (idx < a.nvec) {
+                        *reinterpret_cast<float4*>(pr + idx * 4) = sa[v];
+                        *reinterpret_cast<float4*>(pr + a.ld + idx * 4) = sb[v];
+                    }
+                }
+                return;
+            }
+        }
+    }
+    gamma_row_update<G, V, MODE>(a, R, gl, gmask, self, sa, sb, sx, empty);
 }
 
 template <int G, int V, int U, int MODE, bool CHUNK_REDUCE>
@@ -303,7 +335,7 @@ __global__ void __launch_bounds__(256) gamma_pass_kernel(const GammaArgs a) {
     if constexpr (MODE == 2 && CHUNK_REDUCE) sx = group_sum<G>(sx);   // full mask: the warp is still converged here
     if (!has) return;
     if (pidx < 0) {  // the whole row lives in this segment: finish it here
-        gamma_row_update<G, V, MODE>(a, R, gl, group_mask<G>(lane), self, sa, sb, sx, empty);
+        finish_row<G, V, MODE>(a, R, gl, group_mask<G>(lane), self, sa, sb, sx, empty);
     } else {
         if constexpr (MODE == 2) if (gl == 0) a.partial_x[pidx] = sx;
         float* dst = a.partial + (size_t)pidx * 2 * a.ld;
@@ -385,7 +417,40 @@ __global__ void __launch_bounds__(256) gamma_multi_kernel(const GammaArgs a) {
             }
         }
     }
-    gamma_row_update<G, V, MODE>(a, R, gl, group_mask<G>(lane), self, sa, sb, sx, false);
+    finish_row<G, V, MODE>(a, R, gl, group_mask<G>(lane), self, sa, sb, sx, false);
+}
+
+// Multi-GPU item pass, last step: every rank has parked its user range's row sums in its own `acc` table; the owner of
+// row R adds the ranks' sums -- ONE multimem.ld_reduce per 16 bytes, the addition is done by the NVSwitch -- applies the
+// Gamma update and pushes the new row to every replica with multimem.st.  With mc_acc == NULL the sums in `acc` are
+// already complete (NCCL all-reduce, or a single GPU) and are read with plain loads.  One lane group per row.
+template <int G, int V, int MODE>
+__global__ void __launch_bounds__(256) gamma_combine_kernel(const GammaArgs a, const float* mc_acc, int row_begin, int row_end) {
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int R = row_begin + (int)gid;
+    if (gid >= row_end - row_begin) return;
+    float4 self[V], sa[V], sb[V];
+    const size_t poff = (size_t)(R - a.acc_row_base) * 2 * a.ld;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int idx = gl + v * G;
+        self[v] = sa[v] = sb[v] = f4_zero();
+        if (idx < a.nvec) {
+            self[v] = *reinterpret_cast<const float4*>(a.E_self + (size_t)R * a.ld + idx * 4);
+            if (mc_acc) {
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(sa[v].x), "=f"(sa[v].y), "=f"(sa[v].z), "=f"(sa[v].w) : "l"(mc_acc + poff + idx * 4) : "memory");
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(sb[v].x), "=f"(sb[v].y), "=f"(sb[v].z), "=f"(sb[v].w) : "l"(mc_acc + poff + a.ld + idx * 4) : "memory");
+            } else {
+                sa[v] = ld_stream_f4(a.acc + poff + idx * 4);
+                sb[v] = ld_stream_f4(a.acc + poff + a.ld + idx * 4);
+            }
+        }
+    }
+    gamma_row_update<G, V, MODE>(a, R, gl, group_mask<G>(lane), self, sa, sb, 0.f, false);
 }
 
 static int g_tune_interleave = 0;   // 1 = golden-ratio block interleave of the longest-first order (experiment)
@@ -406,7 +471,7 @@ static int launch_gamma(const GammaArgs& a_in, int mode, cudaStream_t s) {
         const bool interleave = g_tune_interleave > 0;   // measured slower at N=1 and N=8 (profiles/README.md): off
         a.block_stride = 1;
         if (g_tune_interleave == 2 && grid > 2) {
-            a.block_stride = grid - 1;   // shortest segments first (row completions, hence P2P stores, start early)
+            a.block_stride = grid - 1;   // shortest segments first
         } else if (interleave && grid > 2) {
             uint32_t st = (uint32_t)(0.6180339887 * grid) | 1u;   // golden-ratio stride: even spread of every length class
             while (gcd_u32(st, grid) != 1) st += 2;
@@ -446,8 +511,10 @@ static void fill_csr_args(GammaArgs& a, const CsrView& c, int32_t K, int32_t ld)
     a.seg_desc = c.seg_desc;
     a.col = c.col; a.val = c.val; a.multi_row = c.multi_row; a.multi_first = c.multi_first;
     a.n_seg = c.n_seg; a.n_multi = c.n_multi; a.seg_len = c.seg_len; a.row_offset = c.row_offset;
-    a.K = K; a.ld = ld; a.nvec = ld / 4; a.nnz_hint = c.nnz; a.gather_bytes = (int64_t)c.n_cols * ld * 4;
+    a.K = K; a.ld = ld; a.nvec = ld / 4; a.nnz_hint = c.nnz;
+    a.gather_bytes = (int64_t)(c.n_cols - c.col_lo) * ld * 4;   // the span of E_oth this list's ratings point into
     a.scale_oth = nullptr; a.scale_shp = nullptr; a.partial_x = nullptr;
+    a.acc = nullptr; a.acc_in = a.acc_out = 0; a.acc_row_base = 0;
 }
 
 static int dispatch_gamma(const GammaArgs& a, int mode, cudaStream_t s) {
@@ -471,6 +538,15 @@ static int dispatch_gamma(const GammaArgs& a, int mode, cudaStream_t s) {
     if (nv <= 24) return launch_gamma<8, 3, 2>(a, mode, s);
     if (nv <= 32) return launch_gamma<8, 4, 2>(a, mode, s);
     return launch_gamma<16, 4, 2>(a, mode, s);
+}
+
+template <int G, int V>
+static int launch_combine(const GammaArgs& a, const float* mc_acc, int row_begin, int row_end, int mode, cudaStream_t s) {
+    const unsigned grid = (unsigned)cdiv((int64_t)(row_end - row_begin) * G, 256);
+    if (mode == 1) gamma_combine_kernel<G, V, 1><<<grid, 256, 0, s>>>(a, mc_acc, row_begin, row_end);
+    else gamma_combine_kernel<G, V, 0><<<grid, 256, 0, s>>>(a, mc_acc, row_begin, row_end);
+    PMF_LAUNCH_CHECK();
+    return PMF_OK;
 }
 
 }  // namespace pmf
@@ -502,41 +578,66 @@ int pmf_gamma_pass(const pmf_csr* csr, int32_t K, int32_t ld, const float* d_E_o
                    float* d_rte, float shape_prior, float rate_prior, const float* d_rate_prior_vec,
                    float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior,
                    void* d_workspace, void* stream) {
-    return pmf_gamma_pass_p2p(csr, K, ld, d_E_oth, d_E_self, d_shp, d_rte, shape_prior, rate_prior, d_rate_prior_vec,
-                              d_hyper_rate, d_hyper_mean, hyper_shape, hyper_rate_prior, d_workspace, 0, nullptr,
-                              nullptr, stream);
+    return pmf_gamma_pass_acc(csr, K, ld, d_E_oth, d_E_self, d_shp, d_rte, shape_prior, rate_prior, d_rate_prior_vec,
+                              d_hyper_rate, d_hyper_mean, hyper_shape, hyper_rate_prior, d_workspace, nullptr, 0, 0,
+                              stream);
 }
 
-int pmf_gamma_pass_p2p(const pmf_csr* csr, int32_t K, int32_t ld, const float* d_E_oth, float* d_E_self, float* d_shp,
-                       float* d_rte, float shape_prior, float rate_prior, const float* d_rate_prior_vec,
-                       float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior,
-                       void* d_workspace, int32_t n_peers, void* const* h_peer_E_self,
-                       void* const* h_peer_hyper_mean, void* stream) {
-    PMF_REQUIRE(csr != nullptr, "csr is NULL");
+static int check_gamma_tables(int32_t K, int32_t ld, const void* d_E_oth, const void* d_E_self, const void* d_hyper_rate,
+                              const void* d_hyper_mean) {
     PMF_REQUIRE(K >= 1 && ld >= K && ld % 8 == 0 && ld <= 256, "need 1 <= K <= ld <= 256 and ld %% 8 == 0 (K=%d ld=%d)", K, ld);
     PMF_REQUIRE(d_E_oth && d_E_self, "factor tables are NULL");
     PMF_REQUIRE((d_hyper_rate == nullptr) == (d_hyper_mean == nullptr), "hyper_rate and hyper_mean go together");
+    return PMF_OK;
+}
+
+int pmf_gamma_pass_acc(const pmf_csr* csr, int32_t K, int32_t ld, const float* d_E_oth, float* d_E_self, float* d_shp,
+                       float* d_rte, float shape_prior, float rate_prior, const float* d_rate_prior_vec,
+                       float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior,
+                       void* d_workspace, float* d_acc, int32_t acc_row_base, int32_t acc_flags, void* stream) {
+    PMF_REQUIRE(csr != nullptr, "csr is NULL");
+    PMF_TRY(check_gamma_tables(K, ld, d_E_oth, d_E_self, d_hyper_rate, d_hyper_mean));
+    PMF_REQUIRE((acc_flags & ~3) == 0 && (acc_flags == 0 || d_acc != nullptr), "acc_flags=%d needs d_acc", acc_flags);
     const CsrView c = csr_view(csr);
     PMF_REQUIRE(c.n_partial == 0 || d_workspace != nullptr, "workspace is NULL but %d partial sums are needed", c.n_partial);
+    PMF_REQUIRE(acc_flags == 0 || acc_row_base <= c.row_offset, "acc_row_base=%d beyond the first row %d", acc_row_base, c.row_offset);
     GammaArgs a;
     fill_csr_args(a, c, K, ld);
     a.E_oth = d_E_oth; a.E_self = d_E_self; a.shp = d_shp; a.rte = d_rte;
     a.shape_prior = shape_prior; a.rate_prior = rate_prior; a.rate_prior_vec = d_rate_prior_vec;
     a.hyper_rate = d_hyper_rate; a.hyper_mean = d_hyper_mean; a.hyper_shape = hyper_shape;
     a.hyper_rate_prior = hyper_rate_prior; a.partial = (float*)d_workspace;
-    PMF_REQUIRE(n_peers >= -1 && n_peers <= kMaxPeers, "n_peers=%d outside [-1, %d]", n_peers, kMaxPeers);
-    PMF_REQUIRE(n_peers == 0 || h_peer_E_self != nullptr, "peer table pointers are NULL");
+    a.acc = acc_flags ? d_acc : nullptr;
+    a.acc_in = (acc_flags & PMF_ACC_IN) != 0; a.acc_out = (acc_flags & PMF_ACC_OUT) != 0; a.acc_row_base = acc_row_base;
     a.mc_E = nullptr;
-    if (n_peers == -1) {   // multicast mode: h_peer_E_self[0] is the multicast address of E_self
-        a.mc_E = (float*)h_peer_E_self[0];
-        n_peers = 0;
-    }
-    a.n_peers = n_peers;
-    for (int pr = 0; pr < kMaxPeers; ++pr) {
-        a.peer_E[pr] = pr < n_peers ? (float*)h_peer_E_self[pr] : nullptr;
-        a.peer_hyper_mean[pr] = (pr < n_peers && h_peer_hyper_mean) ? (float*)h_peer_hyper_mean[pr] : nullptr;
-    }
     return dispatch_gamma(a, d_hyper_rate != nullptr ? 1 : 0, (cudaStream_t)stream);
+}
+
+int pmf_gamma_combine(int32_t row_begin, int32_t row_end, int32_t K, int32_t ld, const float* d_acc,
+                      const float* d_mc_acc, int32_t acc_row_base, float* d_E_self, float* d_mc_E_self, float* d_shp,
+                      float* d_rte, float shape_prior, float rate_prior, const float* d_rate_prior_vec,
+                      float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior, void* stream) {
+    PMF_TRY(check_gamma_tables(K, ld, d_acc, d_E_self, d_hyper_rate, d_hyper_mean));
+    PMF_REQUIRE(0 <= acc_row_base && acc_row_base <= row_begin && row_begin <= row_end, "bad row range [%d,%d) base %d",
+                row_begin, row_end, acc_row_base);
+    if (row_end == row_begin) return PMF_OK;
+    GammaArgs a = {};
+    a.K = K; a.ld = ld; a.nvec = ld / 4;
+    a.E_self = d_E_self; a.shp = d_shp; a.rte = d_rte;
+    a.shape_prior = shape_prior; a.rate_prior = rate_prior; a.rate_prior_vec = d_rate_prior_vec;
+    a.hyper_rate = d_hyper_rate; a.hyper_mean = d_hyper_mean; a.hyper_shape = hyper_shape;
+    a.hyper_rate_prior = hyper_rate_prior;
+    a.acc = const_cast<float*>(d_acc); a.acc_row_base = acc_row_base;
+    a.mc_E = d_mc_E_self;
+    const int mode = d_hyper_rate != nullptr ? 1 : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nv = a.nvec;
+    if (nv <= 4) return launch_combine<4, 1>(a, d_mc_acc, row_begin, row_end, mode, s);
+    if (nv <= 8) return launch_combine<8, 1>(a, d_mc_acc, row_begin, row_end, mode, s);
+    if (nv <= 16) return launch_combine<8, 2>(a, d_mc_acc, row_begin, row_end, mode, s);
+    if (nv <= 24) return launch_combine<8, 3>(a, d_mc_acc, row_begin, row_end, mode, s);
+    if (nv <= 32) return launch_combine<8, 4>(a, d_mc_acc, row_begin, row_end, mode, s);
+    return launch_combine<16, 4>(a, d_mc_acc, row_begin, row_end, mode, s);
 }
 
 int pmf_gamma_pass_ext(const pmf_csr* csr, int32_t K, int32_t ld, const float* d_E_oth, const float* d_scale_oth,
@@ -555,8 +656,7 @@ int pmf_gamma_pass_ext(const pmf_csr* csr, int32_t K, int32_t ld, const float* d
     a.partial = (float*)d_workspace;
     a.partial_x = a.partial ? a.partial + (size_t)c.n_partial * 2 * ld : nullptr;
     a.scale_oth = d_scale_oth; a.scale_shp = d_scale_shp;
-    a.mc_E = nullptr; a.n_peers = 0;
-    for (int pr = 0; pr < kMaxPeers; ++pr) { a.peer_E[pr] = nullptr; a.peer_hyper_mean[pr] = nullptr; }
+    a.mc_E = nullptr;
     return dispatch_gamma(a, 2, (cudaStream_t)stream);
 }
 

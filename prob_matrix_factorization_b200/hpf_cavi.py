@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 from . import _cabi
-from ._engine import EvalSet, GammaEngine, Trace, eval_stats, normalise_ids, predict, table_to_host
+from ._engine import EvalSet, GammaEngine, Trace, eval_stats, normalise_ids, predict, row_stride, table_to_host
 from .poisson_mf_cavi import _DeviceBacked
 from .ratings import DEFAULT_SEG_LEN, DeviceRatings, to_device
 
@@ -67,6 +67,8 @@ class HPF_CAVI(_DeviceBacked):
         self._shard = shard
         self._seg_len = seg_len
         self._auto_close = True
+        self._ratings_kw = {}     # extra DeviceRatings arguments (tile overrides; experiments / tests)
+        self._engine_kw = {}      # extra GammaEngine arguments (exchange, item_chunks)
         self.n_iter_ = 0
         self.val_rmse_history_ = []
         self._init = None
@@ -130,11 +132,13 @@ class HPF_CAVI(_DeviceBacked):
             self._engine.close()          # collective on multi-GPU runs: every rank re-fits together
         tr.mark("close previous engine")
         dr = DeviceRatings(user_ids, item_ids, ratings, self.n_users, self.n_items, self._device,
-                           seg_len=self._seg_len, shard=self._shard)
-        tr.mark("ratings H2D + grouping + shard")
+                           seg_len=self._seg_len, shard=self._shard,
+                           row_bytes=None if self._allocation == "digamma" else 4 * row_stride(cfg.n_factors),
+                           **self._ratings_kw)
+        tr.mark("ratings H2D + routing + grouping")
         hyper = {"user_shape": float(init["gamma_a_xi"]), "user_rate_prior": float(cfg.b_prime),
                  "item_shape": float(init["gamma_a_eta"]), "item_rate_prior": float(cfg.d_prime)}
-        eng = GammaEngine(dr, cfg.n_factors, cfg.a, cfg.c, None, None, hyper=hyper)
+        eng = GammaEngine(dr, cfg.n_factors, cfg.a, cfg.c, None, None, hyper=hyper, **self._engine_kw)
         tr.mark("engine tables (+ symmetric memory / IPC)")
         eng.load_means(init["E_theta"], init["E_beta"], init["E_xi"], init["E_eta"])
         tr.mark("initial factors H2D")
@@ -150,15 +154,17 @@ class HPF_CAVI(_DeviceBacked):
         self.val_rmse_history_ = []
         ev = None
         if val is not None:
-            ev = EvalSet(val[0], val[1], val[2], self.n_users, self.n_items, eng.dev)
+            ev = EvalSet(val[0], val[1], val[2], self.n_users, self.n_items, eng.dev, user_range=eng.eval_range())
         prev_val_rmse = None
+        # the Gamma shape/rate tables are outputs only: they are written by the sweep that can be the last one
+        params_every_sweep = self._track_elbo or (ev is not None and cfg.tol is not None)
         for it in range(1, cfg.max_iter + 1):
             if cfg.verbose:
                 print(f"\nHPF_CAVI iteration {it}/{cfg.max_iter}")
             if self._allocation == "digamma":
                 eng.sweep_digamma()
             else:
-                eng.sweep()
+                eng.sweep(write_params=params_every_sweep or it == cfg.max_iter)
             self.n_iter_ = it
             if self._track_elbo:
                 self.elbo_history_.append(eng.elbo(cfg, refresh_geomean=self._allocation != "digamma")[0])

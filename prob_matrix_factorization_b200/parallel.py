@@ -1,11 +1,12 @@
-"""Multi-GPU plumbing: one process per GPU, ratings sharded by nonzero, factors replicated.
+"""Multi-GPU plumbing: one process per GPU, ratings sharded by nonzero along USER ranges.
 
 The reference is single-process; this is new.  Each rank owns a
-contiguous, nnz-balanced range of user rows (for the user pass) and of item rows (for the item
-pass).  After a pass every rank holds fresh factor rows only for its own range, so the per-pass
-"statistics combine" is an all-gather of owned rows of the replicated table (variable sizes),
-not an all-reduce of zero-padded statistics: 2.5x fewer bytes over NVLink for the same result
-(SURVEY.md §8e).  ``torch.distributed`` is the transport (NCCL on GPUs, gloo in CPU tests).
+contiguous, nnz-balanced range of users and holds exactly those users' ratings.  The user pass is
+then local (no exchange: E_theta rows are only ever read by their owner's item pass); the item pass
+leaves per-rank partial row sums over all items, which are added across ranks -- inside the NVSwitch
+by ``pmf_gamma_combine`` (multimem.ld_reduce), or by an NCCL all-reduce in the unfused baseline -- and
+the new E_beta rows are replicated.  ``torch.distributed`` is the transport for set-up and the
+baseline (NCCL on GPUs, gloo in CPU tests).
 """
 from __future__ import annotations
 
@@ -51,6 +52,30 @@ def balanced_row_bounds(row_ptr, parts):
         bounds[p] = max(lo, bounds[p - 1])
     bounds[parts] = n_rows
     return bounds
+
+
+def balanced_bounds_from_counts(counts, parts):
+    """Row-aligned, nnz-balanced boundaries from per-row rating counts (host; int64[parts+1]).
+
+    Same rule as pmf_csr_partition / balanced_row_bounds: boundary p is the first row whose start offset is
+    >= nnz*p/parts."""
+    counts = np.asarray(counts, dtype=np.int64)
+    row_ptr = np.zeros(len(counts) + 1, dtype=np.int64)
+    np.cumsum(counts, out=row_ptr[1:])
+    return balanced_row_bounds(row_ptr, parts)
+
+
+def owned_item_ranges(n_items, chunks, world, rank):
+    """Item rows whose combine step `rank` performs: the rank's share of each of `chunks` equal item ranges.
+
+    Chunk c = [n_items*c//chunks, n_items*(c+1)//chunks); inside it rank r owns the r-th of `world` equal parts.
+    (Chunks exist so that the cross-rank combine of one chunk overlaps the item pass of the next.)"""
+    out = []
+    for c in range(chunks):
+        lo, hi = n_items * c // chunks, n_items * (c + 1) // chunks
+        n = hi - lo
+        out.append((lo + n * rank // world, lo + n * (rank + 1) // world))
+    return out
 
 
 def replicate_from_slices(host, device, world, rank, dtype=None, group=None):
@@ -101,62 +126,3 @@ class RowExchange:
             for g, v in enumerate(views):
                 if v.numel() > 0:
                     dist.broadcast(v, src=dist.get_global_rank(self.group, g) if self.group else g, group=self.group)
-
-
-class _CudaArray:
-    """Minimal __cuda_array_interface__ carrier so torch can view library-allocated device memory."""
-
-    def __init__(self, ptr, shape, typestr="<f4"):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
-                                         "version": 2, "strides": None}
-
-
-class PeerTable:
-    """A replicated float32 table whose copies on the other ranks are mapped into this process (CUDA IPC).
-
-    ``local`` is a torch view of this rank's copy; ``peer_ptrs`` are the other ranks' copies as raw device
-    pointers reachable over NVLink (P2P loads/stores).  Used by the fused pass+exchange kernel
-    (``pmf_gamma_pass_p2p``): each rank stores the rows it owns straight into every replica.
-    """
-
-    def __init__(self, shape, device, group=None):
-        import ctypes as C
-
-        from . import _cabi
-        self.device = torch.device(device)
-        self.shape = tuple(int(s) for s in shape)
-        nbytes = 4 * int(np.prod(self.shape))
-        self._ptr = C.c_void_p()
-        handle = C.create_string_buffer(64)
-        with torch.cuda.device(self.device):
-            _cabi.call("pmf_ipc_alloc", max(nbytes, 64), C.byref(self._ptr), handle)
-            self.local = torch.as_tensor(_CudaArray(self._ptr.value, self.shape), device=self.device)
-            self.local.zero_()
-        world = dist.get_world_size(group)
-        self.rank = dist.get_rank(group)
-        handles = [None] * world
-        dist.all_gather_object(handles, handle.raw, group=group)
-        self._opened = []
-        self.peer_ptrs = []
-        with torch.cuda.device(self.device):
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    continue
-                p = C.c_void_p()
-                _cabi.call("pmf_ipc_open", C.create_string_buffer(h, 64), C.byref(p))
-                self._opened.append(p)
-                self.peer_ptrs.append(p.value)
-        self.peer_array = (C.c_void_p * max(1, len(self.peer_ptrs)))(*self.peer_ptrs)
-
-    def close(self):
-        from . import _cabi
-        lib = _cabi.load()
-        with torch.cuda.device(self.device):
-            torch.cuda.synchronize()
-            for p in self._opened:
-                lib.pmf_ipc_close(p)
-            self._opened = []
-            if self._ptr is not None and self._ptr.value:
-                self.local = None
-                lib.pmf_ipc_free(self._ptr)
-                self._ptr = None

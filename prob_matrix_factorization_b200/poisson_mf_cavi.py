@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from ._engine import EvalSet, GammaEngine, eval_stats, normalise_ids, predict, table_to_host
+from ._engine import EvalSet, GammaEngine, eval_stats, normalise_ids, predict, row_stride, table_to_host
 from .ratings import DEFAULT_SEG_LEN, DeviceRatings, to_device
 
 
@@ -91,6 +91,8 @@ class PoissonMFCAVI(_DeviceBacked):
         self._shard = shard
         self._seg_len = seg_len
         self._auto_close = True
+        self._ratings_kw = {}     # extra DeviceRatings arguments (tile overrides; experiments / tests)
+        self._engine_kw = {}      # extra GammaEngine arguments (exchange, item_chunks)
         self.n_iter_ = 0
         self.val_rmse_history_ = []
 
@@ -153,8 +155,9 @@ class PoissonMFCAVI(_DeviceBacked):
         if self._engine is not None:
             self._engine.close()          # collective on multi-GPU runs: every rank re-fits together
         dr = DeviceRatings(user_ids, item_ids, ratings, self.n_users, self.n_items, self._device,
-                           seg_len=self._seg_len, shard=self._shard)
-        eng = GammaEngine(dr, cfg.n_factors, cfg.a0, cfg.a0, cfg.b0, cfg.b0)
+                           seg_len=self._seg_len, shard=self._shard, row_bytes=4 * row_stride(cfg.n_factors),
+                           **self._ratings_kw)
+        eng = GammaEngine(dr, cfg.n_factors, cfg.a0, cfg.a0, cfg.b0, cfg.b0, **self._engine_kw)
         eng.load_means(init["E_theta"], init["E_beta"])
         self._engine = eng
         self._invalidate()
@@ -163,12 +166,14 @@ class PoissonMFCAVI(_DeviceBacked):
         self.val_rmse_history_ = []
         ev = None
         if val is not None:
-            ev = EvalSet(val[0], val[1], val[2], self.n_users, self.n_items, eng.dev)
+            ev = EvalSet(val[0], val[1], val[2], self.n_users, self.n_items, eng.dev, user_range=eng.eval_range())
         prev_val_rmse = None
+        # the Gamma shape/rate tables are outputs only: they are written by the sweep that can be the last one
+        params_every_sweep = ev is not None and cfg.tol is not None
         for it in range(1, cfg.max_iter + 1):
             if cfg.verbose:
                 print(f"\nCAVI iteration {it}/{cfg.max_iter}")
-            eng.sweep()
+            eng.sweep(write_params=params_every_sweep or it == cfg.max_iter)
             self.n_iter_ = it
             if ev is not None:
                 st = self._eval(ev)

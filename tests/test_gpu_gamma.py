@@ -123,3 +123,67 @@ def test_zero_iterations_and_rate_floor():
     m.fit_arrays(u, i, x, init)
     ref = CO.poisson_sweeps(u, i, x, 3, 3, 4, 0.3, 1.0, 1, init["E_theta"], init["E_beta"])
     assert rel_max(m.E_theta, ref["E_theta"]) < TOL and rel_max(m.E_beta, ref["E_beta"]) < TOL
+
+
+@pytest.mark.parametrize("model", ["poisson", "hpf"])
+@pytest.mark.parametrize("user_tiles,item_tiles,seg_len", [(1, 4, 64), (3, 1, 16), (3, 5, 8), (2, 2, 128)])
+def test_tiled_passes_vs_oracle(model, user_tiles, item_tiles, seg_len):
+    """The tiled form of the passes (ratings split by the id range of the gathered table, row sums carried across the
+    tiles by pmf_gamma_pass_acc): same results as the untiled reference algorithm.  seg_len 8/16 puts multi-segment
+    rows (the scratch + gamma_multi_kernel path) into every tile; rows without ratings in a tile exercise the
+    skip / zero / finish-from-running-sums branches."""
+    from prob_matrix_factorization_b200 import synth
+    from prob_matrix_factorization_b200.hpf_cavi import HPF_CAVI, HPF_CAVI_Config
+    from prob_matrix_factorization_b200.poisson_mf_cavi import PoissonMFCAVI, PoissonMFCAVIConfig
+    N, M, nnz, K, T = 4000, 2500, 50_000, 20, 10
+    u, i, x = synth.make_ratings(N, M, nnz, seed=321)
+    hp = dict(a=0.3, a_prime=5.0, b_prime=5.0, c=0.3, c_prime=5.0, d_prime=5.0)
+    if model == "poisson":
+        m = PoissonMFCAVI(PoissonMFCAVIConfig(n_factors=K, a0=0.1, b0=0.5, max_iter=T, tol=None, verbose=False), seg_len=seg_len)
+    else:
+        x = x + 1.0
+        m = HPF_CAVI(HPF_CAVI_Config(n_factors=K, max_iter=T, tol=None, verbose=False, **hp), seg_len=seg_len)
+    m._ratings_kw = dict(user_pass_tiles=user_tiles, item_pass_tiles=item_tiles)
+    m.n_users, m.n_items = N, M
+    init = m._initial_state()
+    m.fit_arrays(u, i, x, init)
+    assert len(m._engine.r.user_tiles) == user_tiles and len(m._engine.r.item_tiles) == item_tiles
+    assert sum(g.nnz for g in m._engine.r.user_tiles) == nnz and sum(g.nnz for g in m._engine.r.item_tiles) == nnz
+    if model == "poisson":
+        ref = CO.poisson_sweeps(u, i, x, N, M, K, 0.1, 0.5, T, init["E_theta"], init["E_beta"])
+        names = ("a_theta", "b_theta", "a_beta", "b_beta", "E_theta", "E_beta")
+    else:
+        ref = CO.hpf_sweeps(u, i, x, N, M, K, hp, T, init)
+        names = ("gamma_a_theta", "gamma_b_theta", "gamma_a_beta", "gamma_b_beta", "gamma_b_xi", "gamma_b_eta",
+                 "E_theta", "E_beta", "E_xi", "E_eta")
+    for k in names:
+        assert rel_max(getattr(m, k), ref[k]) < TOL, k
+
+
+def test_coo_partition_is_stable():
+    """pmf_coo_partition (routing of ratings to tiles / owner ranks): bit-exact stable bucket partition."""
+    import torch
+    from prob_matrix_factorization_b200 import synth
+    from prob_matrix_factorization_b200.ratings import coo_partition
+    N, M, nnz = 5000, 3000, 200_001
+    u, i, x = synth.make_ratings(N, M, nnz, seed=5)
+    ud, idv, xd = (torch.from_numpy(a).cuda() for a in (u, i, x))
+    for by_item, ids, bounds in ((False, u, [0, 17, 17, 2500, 4999, 5000]), (True, i, [0, 3000]), (True, i, [0, 1, 2, 1000, 3000])):
+        uo, io, xo, offs = coo_partition(ud, idv, xd, np.array(bounds), by_item)
+        bucket = np.searchsorted(np.array(bounds[1:]), ids, side="right")
+        order = np.argsort(bucket, kind="stable")
+        assert np.array_equal(uo.cpu().numpy(), u[order]) and np.array_equal(io.cpu().numpy(), i[order])
+        assert np.array_equal(xo.cpu().numpy(), x[order])
+        assert np.array_equal(offs, np.concatenate([[0], np.cumsum(np.bincount(bucket, minlength=len(bounds) - 1))]))
+
+
+def test_count_keys():
+    import torch
+    from prob_matrix_factorization_b200 import _cabi, synth
+    u, _, _ = synth.make_ratings(7000, 10, 100_003, seed=9)
+    ud = torch.from_numpy(u).cuda()
+    counts = torch.full((7000,), -1, dtype=torch.int32, device="cuda")
+    _cabi.call("pmf_count_keys", ud.data_ptr(), ud.numel(), 7000, counts.data_ptr(), _cabi.stream_ptr())
+    assert np.array_equal(counts.cpu().numpy(), np.bincount(u, minlength=7000))
+    with pytest.raises(_cabi.PMFError):
+        _cabi.call("pmf_count_keys", ud.data_ptr(), ud.numel(), 6999, counts.data_ptr(), _cabi.stream_ptr())
