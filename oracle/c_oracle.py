@@ -34,6 +34,8 @@ def lib():
         L.orc_hpf_sweeps.argtypes = [i32p, i32p, f64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [C.c_double] * 6 + \
                                     [C.c_int32] + [f64p] * 10 + [C.c_int, C.POINTER(C.c_double)]
         L.orc_predict.argtypes = [i64p, i64p, C.c_int64, f64p, C.c_int32, f64p, C.c_int32, C.c_int32, f64p]
+        L.orc_gauss_sweeps.argtypes = [i32p, i32p, f64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [C.c_double] * 4 + \
+                                      [C.c_int32, C.c_int32] + [f64p] * 6 + [C.c_int, C.POINTER(C.c_double)]
         L.orc_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -76,6 +78,20 @@ def hpf_sweeps(u, i, x, N, M, K, cfg, sweeps, init, threads=0):
                          bx, be, threads, C.byref(secs))
     return dict(E_theta=Et, E_beta=Eb, E_xi=Ex, E_eta=Ee, gamma_a_theta=at, gamma_b_theta=bt, gamma_a_beta=ab,
                 gamma_b_beta=bb, gamma_b_xi=bx, gamma_b_eta=be, sweep_seconds=secs.value)
+
+
+def gauss_sweeps(u, i, x, N, M, K, sigma2, eta_theta2, eta_beta2, eta_bias2, sweeps, init, bias=True, threads=0):
+    """`init` as produced by oracle.pmf_oracle.gauss_init (m_theta, m_beta, V_theta, V_beta, m_user_bias, m_item_bias)."""
+    u = np.ascontiguousarray(u, dtype=np.int32); i = np.ascontiguousarray(i, dtype=np.int32)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    st = {k: np.array(init[k], dtype=np.float64, order="C") for k in
+          ("m_theta", "m_beta", "V_theta", "V_beta", "m_user_bias", "m_item_bias")}
+    secs = C.c_double(0.0)
+    lib().orc_gauss_sweeps(u, i, x, len(x), N, M, K, sigma2, eta_theta2, eta_beta2, eta_bias2, int(bool(bias)), sweeps,
+                           st["m_theta"], st["m_beta"], st["V_theta"], st["V_beta"], st["m_user_bias"], st["m_item_bias"],
+                           threads, C.byref(secs))
+    st["sweep_seconds"] = secs.value
+    return st
 
 
 def predict(users, items, F_user, F_item):

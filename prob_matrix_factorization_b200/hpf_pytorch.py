@@ -25,6 +25,8 @@ import torch.nn.functional as F
 from . import _cabi
 
 
+LAZY_LAUNCHES_PER_STEP = 3     # pmf_hpf_map_lazy_epoch: catch-up, loss+gradient, touched-row Adam
+
 @dataclass
 class HPF_PyTorch_Config:
     n_factors: int = 20
@@ -144,7 +146,7 @@ class HPF_PyTorch(nn.Module):
 
     # -- loader-free training ------------------------------------------------------------------------
     def fit_epochs(self, users, items, ratings, epochs=None, batch_size=4096, lr=None, shuffle=True, on_epoch=None,
-                   lazy=False):
+                   lazy=False, stats=None):
         """The scripts' loop (compare_models.py:299-313) without the DataLoader.
 
         Per epoch the shuffle is torch's own: ``DataLoader.__iter__`` draws ``_base_seed`` then
@@ -156,7 +158,8 @@ class HPF_PyTorch(nn.Module):
         (``pmf_hpf_map_lazy_epoch``; same arithmetic as the dense update, the whole epoch is enqueued by one C
         call).  It moves ~250x fewer bytes but is currently SLOWER at C4 (133 vs 97 ms/epoch, profiles/README.md):
         the replay is a dependent chain of IEEE sqrt + divides per skipped step.  Returns the list of epoch
-        losses (sum of mini-batch losses, as the scripts print).
+        losses (sum of mini-batch losses, as the scripts print).  ``stats`` (a dict) receives ``device_ms`` -- CUDA-event
+        time of the epochs, uploads excluded -- and ``launches`` (this library's kernels).
         """
         cfg = self.config
         epochs = cfg.epochs if epochs is None else epochs
@@ -172,9 +175,17 @@ class HPF_PyTorch(nn.Module):
         grads = st.setdefault("g", [torch.zeros_like(p) for p in params])
         beta1, beta2, eps = 0.9, 0.999, 1e-8
         losses = []
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(torch.cuda.current_stream(dev))
+        steps_per_epoch = (n + batch_size - 1) // batch_size
         if lazy:
-            return self._fit_epochs_lazy(u_all, i_all, r_all, epochs, batch_size, lr, shuffle, on_epoch, st, params,
-                                         grads, (beta1, beta2, eps))
+            losses = self._fit_epochs_lazy(u_all, i_all, r_all, epochs, batch_size, lr, shuffle, on_epoch, st, params,
+                                           grads, (beta1, beta2, eps))
+            ev1.record(torch.cuda.current_stream(dev))
+            if stats is not None:
+                torch.cuda.synchronize(dev)
+                stats.update(device_ms=ev0.elapsed_time(ev1), launches=epochs * (steps_per_epoch * LAZY_LAUNCHES_PER_STEP + 1))
+            return losses
         with torch.cuda.device(dev), torch.no_grad():
             for ep in range(epochs):
                 if shuffle:
@@ -202,6 +213,10 @@ class HPF_PyTorch(nn.Module):
                 losses.append(float(acc.item()))
                 if on_epoch is not None:
                     on_epoch(ep, losses[-1])
+        ev1.record(torch.cuda.current_stream(dev))
+        if stats is not None:
+            torch.cuda.synchronize(dev)
+            stats.update(device_ms=ev0.elapsed_time(ev1), launches=epochs * steps_per_epoch * 5)   # loss+grad, 4 x Adam
         self.check_ids()
         return losses
 

@@ -144,7 +144,7 @@ class Grouped:
         return torch.empty(self.workspace_bytes(ld) // 4, dtype=torch.float32, device=self.device)
 
 
-DEFAULT_TILE_MB = 64    # target size of the slice of a factor table one tile gathers from (about half the 126 MB L2)
+DEFAULT_TILE_MB = 128   # target size of the slice of a factor table one tile gathers from (about the 126 MB L2; measured best at C5)
 
 
 def tile_bounds(lo, hi, row_bytes, tile_bytes=None, n_tiles=None):

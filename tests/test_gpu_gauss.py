@@ -71,3 +71,29 @@ def test_gaussian_vs_oracle(K, seg_len, bias):
     keys = ["m_theta", "V_theta", "m_beta", "V_beta"] + (["m_user_bias", "m_item_bias"] if bias else [])
     for k in keys:
         assert rel_max(getattr(m, k), ref[k]) < TOL, (k, K)
+
+
+@pytest.mark.parametrize("bias", [True, False])
+def test_gaussian_c1_full_size(bias):
+    """BASELINE configs[0] at its real shape (gaussian_mf K=10, 20k users x 10k recipes x 200k ratings, hyper-parameters of
+    best_hyperparams.txt:3), 20 sweeps, against the oracle's C port (pinned on the reference's outputs at 1e-10)."""
+    from oracle import c_oracle as CO
+    from prob_matrix_factorization_b200 import synth
+    from prob_matrix_factorization_b200.gaussian_mf_cavi_bias import GaussianMFCAVI, GaussianMFCAVIConfig
+    from prob_matrix_factorization_b200 import gaussian_mf_cavi as NB
+    w, (u, i, x) = synth.workload_ratings("c1")
+    K, T = w.n_factors, 20
+    mean = float(x.mean())
+    xc = x.astype(np.float64) - mean                       # compare_models.py:54-58: the caller centres the ratings
+    hp = dict(sigma2=0.5, eta_theta2=0.1, eta_beta2=0.1)
+    if bias:
+        m = GaussianMFCAVI(GaussianMFCAVIConfig(n_factors=K, eta_bias2=0.1, max_iter=T, random_state=42, verbose=False, **hp))
+    else:
+        m = NB.GaussianMFCAVI(NB.GaussianMFCAVIConfig(n_factors=K, max_iter=T, random_state=42, verbose=False, **hp))
+    m.fit(frame(u, i, xc), global_mean=mean)
+    assert (m.n_users, m.n_items) == (w.n_users, w.n_items)
+    init = O.gauss_init(w.n_users, w.n_items, K, 42)
+    ref = CO.gauss_sweeps(u, i, xc, w.n_users, w.n_items, K, 0.5, 0.1, 0.1, 0.1, T, init, bias=bias)
+    keys = ["m_theta", "V_theta", "m_beta", "V_beta"] + (["m_user_bias", "m_item_bias"] if bias else [])
+    for k in keys:
+        assert rel_max(getattr(m, k), ref[k]) < TOL, k

@@ -84,6 +84,19 @@ def test_gauss_sweeps(golden, name, bias):
         assert abs(lpl - g["test_lpl"]) < 1e-9 * abs(g["test_lpl"])
 
 
+@pytest.mark.parametrize("name,bias", [("gaussian_bias", True), ("gaussian_nobias", False)])
+def test_gauss_sweeps_c_port(golden, name, bias):
+    """oracle/pmf_oracle.c::orc_gauss_sweeps (Gauss-Jordan inverse instead of LAPACK) against the reference's outputs."""
+    from oracle import c_oracle as CO
+    g = golden(name)
+    init = O.gauss_init(g["n_users"], g["n_items"], g["K"], g["seed"])
+    st = CO.gauss_sweeps(g["u"], g["i"], g["x"], g["n_users"], g["n_items"], g["K"], g["sigma2"], g["eta_theta2"],
+                         g["eta_beta2"], g.get("eta_bias2", 1.0), g["T"], init, bias=bias)
+    keys = ["m_theta", "V_theta", "m_beta", "V_beta"] + (["m_user_bias", "m_item_bias"] if bias else [])
+    for k in keys:
+        assert rel_max(st[k], g[k]) < 1e-10, k
+
+
 def test_hpf_map_loss_and_grads(golden):
     g = golden("hpf_pytorch")
     cfg = {k: g[k] for k in ("a", "a_prime", "b_prime", "c", "c_prime", "d_prime")}
