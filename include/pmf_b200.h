@@ -290,6 +290,13 @@ typedef struct pmf_lazy_adam {
     int32_t *last_user, *last_item, *claim_user, *claim_item, *touched_user, *touched_item, *counters;
     const float *step_size, *bc2_sqrt;
     float beta1, beta2, eps;
+    /* Closed-form catch-up (both or neither; NULL = replay skipped steps one by one).  float64, indexed by step like
+     * step_size, zero beyond the last step s_max of the call:
+     *   tail1[s] = sum_{s < t <= s_max} step_size[t] bc2_sqrt[t]   (beta1/sqrt(beta2))^(t-s)
+     *   tail2[s] = sum_{s < t <= s_max} step_size[t] bc2_sqrt[t]^2 (beta1/beta2)^(t-s)
+     * A run of J zero-gradient steps after step s then moves p by (m/sqrt(v)) [W1 - eps/sqrt(v) W2], W = tail[s] -
+     * ratio^J tail[s+J], and decays m, v by beta^J (first order in eps/sqrt(v); runs where that exceeds 1e-3 are replayed). */
+    const double *tail1, *tail2;
 } pmf_lazy_adam;
 /* One pass over n (already shuffled) ratings in mini-batches of `batch`: per step catch the batch's rows up,
  * fused loss+gradient, Adam step on the touched rows.  step0 = steps taken so far; adds the losses to *d_loss. */

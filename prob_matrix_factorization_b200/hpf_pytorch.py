@@ -220,7 +220,8 @@ class HPF_PyTorch(nn.Module):
         self.check_ids()
         return losses
 
-    def _fit_epochs_lazy(self, u_all, i_all, r_all, epochs, batch_size, lr, shuffle, on_epoch, st, params, grads, hyp):
+    def _fit_epochs_lazy(self, u_all, i_all, r_all, epochs, batch_size, lr, shuffle, on_epoch, st, params, grads, hyp,
+                         closed_form=True):
         import ctypes as C
         beta1, beta2, eps = hyp
         cfg, dev, n = self.config, self.theta_uncons.device, u_all.numel()
@@ -233,6 +234,15 @@ class HPF_PyTorch(nn.Module):
         bc2 = np.sqrt(1.0 - beta2 ** s_idx).astype(np.float32)
         step_size[0], bc2[0] = 0.0, 1.0
         tab = (torch.from_numpy(step_size).to(dev), torch.from_numpy(bc2).to(dev))
+        # closed-form catch-up tables (include/pmf_b200.h pmf_lazy_adam): backward recurrences tail[s] = r (c[s+1] + tail[s+1])
+        tails = []
+        if closed_form:
+            for c, r in ((step_size.astype(np.float64) * bc2, beta1 / math.sqrt(beta2)),
+                         (step_size.astype(np.float64) * bc2.astype(np.float64) ** 2, beta1 / beta2)):
+                tail = np.zeros(total + 2, dtype=np.float64)
+                for s_ in range(total - 1, -1, -1):
+                    tail[s_] = r * (c[s_ + 1] + tail[s_ + 1])
+                tails.append(torch.from_numpy(tail).to(dev))
         i32 = lambda k: torch.zeros(k, dtype=torch.int32, device=dev)
         if "last_user" not in st:
             st.update(last_user=i32(self.n_users), last_item=i32(self.n_items), claim_user=i32(self.n_users),
@@ -249,6 +259,7 @@ class HPF_PyTorch(nn.Module):
                       ("counters", touched[2]), ("step_size", tab[0]), ("bc2_sqrt", tab[1])):
             setattr(S, nm, t.data_ptr())
         S.beta1, S.beta2, S.eps = beta1, beta2, eps
+        S.tail1, S.tail2 = (tails[0].data_ptr(), tails[1].data_ptr()) if closed_form else (None, None)
         losses = []
         id_bytes = 8 if u_all.dtype == torch.int64 else 4
         with torch.cuda.device(dev), torch.no_grad():
