@@ -636,7 +636,7 @@ def run_cavi(job, name):
                               + ("inputs larger than L2, no flush" if ws_gb > 0.5 else
                                  "comparable to L2 -- tables stay L2-resident between sweeps, as they do in a real fit; "
                                  "no flush (a flush would time a cold start no training loop sees)")),
-                       "seg_len": eng.r.seg_len},
+                       "seg_len": {"user_pass": eng.r.seg_len_user, "item_pass": eng.r.seg_len_item}},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_fit_df": e2e_df, "parity_check": parity,
             "gpu_launches": (eng.launches_per_sweep + (len(eng.r.user_tiles) + 3 if with_elbo else 0)) * steps, "clocks": clocks}
     emit(line)

@@ -233,6 +233,26 @@ int pmf_eval_stats(const int32_t* d_users, const int32_t* d_items, const float* 
                    int32_t K, int32_t ld, const float* d_b_user, const float* d_b_item,
                    float global_mean, int32_t drop_invalid, double* d_out, void* stream);
 
+/* ---- f2: device-side training loop (sweeps + validation + early stopping as one CUDA graph) -----------------------
+ * Replaces the per-iteration host decision of hpf_cavi.py:196-211 / poisson_mf_cavi.py:200-217 /
+ * gaussian_mf_cavi_bias.py:268-284.  pmf_loop_begin puts `stream` (not the legacy default stream) into capture INTO the
+ * body of a WHILE conditional graph node; the caller then enqueues ONE iteration on that stream (pass kernels,
+ * pmf_eval_stats into d_eval_out, ...) and finally pmf_loop_decide, whose kernel -- per executed iteration -- increments
+ * *d_iter, stores rmse = sqrt(d_eval_out[1]/d_eval_out[0]) in d_history[*d_iter - 1] and keeps the loop going while
+ * *d_iter < max_iter and the stopping rule has not fired (has_tol != 0; improvement = previous - current rmse):
+ *   rule 0: stop when improvement < tol (Poisson MF / HPF, fires on negative improvement);
+ *   rule 1: stop when 0 <= improvement < tol (Gaussian MF).
+ * d_eval_out == NULL: no validation, exactly max_iter iterations.  pmf_loop_end ends the capture and instantiates;
+ * pmf_loop_run launches the whole loop asynchronously on a stream (*d_iter must be zeroed by the caller).
+ * PMF_EUNSUPPORTED when the driver lacks conditional graph nodes (callers fall back to a host loop). */
+typedef struct pmf_loop pmf_loop;
+int pmf_loop_begin(void* stream, pmf_loop** out);
+int pmf_loop_decide(pmf_loop* loop, const double* d_eval_out, int32_t rule, double tol, int32_t has_tol, int32_t max_iter,
+                    int32_t* d_iter, double* d_history, void* stream);
+int pmf_loop_end(pmf_loop* loop);
+int pmf_loop_run(pmf_loop* loop, void* stream);
+int pmf_loop_free(pmf_loop* loop);
+
 /* ---- a5: Gaussian MF CAVI ---------------------------------------------------------------
  * Tables per side: means m[R, ld] (ld = pmf_row_stride(K)); covariances V and second moments
  * Q = V + m m^T as packed lower triangles [R, ldq] (ldq = pmf_gauss_packed_stride(K); element (i,j),

@@ -34,8 +34,13 @@ class LazyAdamState(C.Structure):
                 + [("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("tail1", VP), ("tail2", VP)])
 
 
+PMF_EUNSUPPORTED = -4
+
+
 class PMFError(RuntimeError):
-    """A libpmf_b200 entry point returned a non-zero status."""
+    """A libpmf_b200 entry point returned a non-zero status (``.status``)."""
+
+    status = 0
 
 
 # name -> (restype, argtypes).  Pointers to device memory are passed as integers (c_void_p).
@@ -54,6 +59,11 @@ _PROTOTYPES = {
     "pmf_coo_partition": (C.c_int, [VP, VP, VP, C.c_int64, C.c_int32, c_i32p, C.c_int32, VP, VP, VP,
                                     C.POINTER(C.c_int64), VP]),
     "pmf_trim": (C.c_int, []),
+    "pmf_loop_begin": (C.c_int, [VP, C.POINTER(VP)]),
+    "pmf_loop_decide": (C.c_int, [VP, VP, C.c_int32, C.c_double, C.c_int32, C.c_int32, VP, VP, VP]),
+    "pmf_loop_end": (C.c_int, [VP]),
+    "pmf_loop_run": (C.c_int, [VP, VP]),
+    "pmf_loop_free": (C.c_int, [VP]),
     "pmf_csr_nnz": (C.c_int64, [VP]),
     "pmf_csr_rows": (C.c_int32, [VP]),
     "pmf_csr_row_offset": (C.c_int32, [VP]),
@@ -134,7 +144,9 @@ def load(build_if_missing=True):
 def check(status, what=""):
     if status != 0:
         msg = load().pmf_last_error()
-        raise PMFError(f"libpmf_b200 {what} failed (status {status}): {msg.decode() if msg else '?'}")
+        err = PMFError(f"libpmf_b200 {what} failed (status {status}): {msg.decode() if msg else '?'}")
+        err.status = int(status)
+        raise err
 
 
 def call(name, *args):

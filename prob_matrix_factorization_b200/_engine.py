@@ -121,13 +121,85 @@ class EvalSet:
         self.out = torch.zeros(4 + 2 * MAX_DEVICE_LABELS, dtype=torch.float64, device=device)
 
 
-def eval_stats(ev, F_user, F_item, n_users, n_items, K, ld, b_user=None, b_item=None, global_mean=0.0):
-    """RMSE / macro-MAE / MAE / Poisson LPL of one EvalSet: one fused kernel + one tiny D2H."""
+def eval_stats_launch(ev, F_user, F_item, n_users, n_items, K, ld, b_user=None, b_item=None, global_mean=0.0):
+    """Enqueue the fused evaluation kernel of one EvalSet (statistics land in ``ev.out``; no host round trip)."""
     with torch.cuda.device(F_user.device):
         _cabi.call("pmf_eval_stats", ev.u.data_ptr(), ev.i.data_ptr(), ev.y.data_ptr(), _cabi.ptr(ev.label),
                    ev.n_labels, ev.n, F_user.data_ptr(), n_users, F_item.data_ptr(), n_items, K, ld,
                    _cabi.ptr(b_user), _cabi.ptr(b_item), float(global_mean), int(ev.drop_invalid),
                    ev.out.data_ptr(), _cabi.stream_ptr())
+
+
+class DeviceLoop:
+    """The fit loop as one CUDA graph with a device-side WHILE (pmf_loop_*, csrc/loop.cu): sweeps, validation statistics
+    and the reference's early-stopping rule run back to back on the GPU; the host reads the iteration count and the
+    RMSE history once, at the end.
+
+        loop = DeviceLoop(dev, max_iter, ev_out=ev.out, rule=0, tol=cfg.tol)
+        with loop.body():            # ONE iteration is enqueued (captured, not executed)
+            engine.sweep(...); eval_stats_launch(ev, ...)
+        n_iter, rmse_history = loop.run()
+    """
+
+    def __init__(self, dev, max_iter, ev_out=None, rule=0, tol=None):
+        self.dev = torch.device(dev)
+        self.max_iter = int(max_iter)
+        self.ev_out, self.rule, self.tol = ev_out, int(rule), tol
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.iter = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.history = torch.zeros(max(1, self.max_iter), dtype=torch.float64, device=self.dev)
+        self._h = C.c_void_p()
+
+    def body(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            self.stream.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
+                _cabi.call("pmf_loop_begin", self.stream.cuda_stream, C.byref(self._h))
+                try:
+                    yield self
+                    _cabi.call("pmf_loop_decide", self._h, _cabi.ptr(self.ev_out), self.rule,
+                               0.0 if self.tol is None else float(self.tol), int(self.tol is not None), self.max_iter,
+                               self.iter.data_ptr(), self.history.data_ptr(), self.stream.cuda_stream)
+                    _cabi.call("pmf_loop_end", self._h)
+                except BaseException:
+                    self.free()
+                    raise
+        return ctx()
+
+    def run(self):
+        """Launch the loop and wait for it: (iterations executed, validation RMSE per iteration as float64 NumPy)."""
+        with torch.cuda.device(self.dev):
+            self.iter.zero_()
+            self.stream.wait_stream(torch.cuda.current_stream(self.dev))
+            _cabi.call("pmf_loop_run", self._h, self.stream.cuda_stream)
+            torch.cuda.current_stream(self.dev).wait_stream(self.stream)
+            n = int(self.iter.cpu().item())
+            hist = self.history[:n].cpu().numpy() if self.ev_out is not None else np.zeros(0)
+        return n, hist
+
+    def free(self):
+        if self._h is not None and self._h.value:
+            _cabi.load().pmf_loop_free(self._h)
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def device_loop_enabled():
+    return os.environ.get("PMF_DEVICE_LOOP", "1") != "0"
+
+
+def eval_stats(ev, F_user, F_item, n_users, n_items, K, ld, b_user=None, b_item=None, global_mean=0.0):
+    """RMSE / macro-MAE / MAE / Poisson LPL of one EvalSet: one fused kernel + one tiny D2H."""
+    eval_stats_launch(ev, F_user, F_item, n_users, n_items, K, ld, b_user, b_item, global_mean)
+    with torch.cuda.device(F_user.device):
         if ev.sharded:
             import torch.distributed as dist
             dist.all_reduce(ev.out)                          # float64 sums over the ranks' rows: identical everywhere
@@ -162,6 +234,13 @@ def predict(u_dev, i_dev, F_user, F_item, n_users, n_items, K, ld, b_user=None, 
                    F_item.data_ptr(), n_items, K, ld, _cabi.ptr(b_user), _cabi.ptr(b_item), float(global_mean),
                    int(bool(softplus)), out.data_ptr(), _cabi.stream_ptr())
     return out.cpu().numpy()
+
+
+# Symmetric-memory tables (multi-GPU) are kept for the life of the process and handed to the next engine of the same
+# shape: allocating + rendezvous of the two tables costs ~0.5 s per fit and releasing them another ~0.4 s (measured at
+# 2 GPUs, profiles/README.md) -- more than 20 sweeps of the 100 M-rating config.  One entry per table name: a fit
+# with other shapes replaces it.
+_SYMM_CACHE = {}
 
 
 class GammaEngine:
@@ -213,6 +292,8 @@ class GammaEngine:
             if flag.item() < 1.0:
                 import warnings
                 warnings.warn(f"multicast combine unavailable ({why or 'on another rank'}); using the NCCL all-reduce")
+                for entry in self._symm.values():
+                    entry[3]["busy"] = False
                 self._symm = {}
                 self.exchange = "nccl"
         # E_theta: during a sharded fit only this rank's rows [user_lo, user_hi) are live (nobody else reads them)
@@ -237,7 +318,7 @@ class GammaEngine:
             self.rate_xi = self.E_xi = self.rate_eta = self.E_eta = None
         # item rows in chunks (multicast combine only): chunk c's combine overlaps chunk c+1's pass
         if item_chunks is None:
-            item_chunks = int(os.environ.get("PMF_ITEM_CHUNKS", 4))
+            item_chunks = ratings.item_chunks
         self.item_chunks = max(1, min(int(item_chunks), self.M)) if self.exchange == "mc" else 1
         if self.item_chunks > 1:
             C_ = self.item_chunks
@@ -331,12 +412,21 @@ class GammaEngine:
         import torch.distributed._symmetric_memory as symm_mem
         group = dist.group.WORLD
         for name, shape in (("E_beta", (self.M, self.ld)), ("acc_item", (self.M, 2 * self.ld))):
+            key = (name, self.dev.index)
+            hit = _SYMM_CACHE.get(key)
+            if hit is not None and not hit["busy"] and tuple(hit["t"].shape) == shape and hit["group"] == group.group_name:
+                hit["busy"] = True
+                self._symm[name] = (hit["t"], hit["hdl"], hit["mc"], hit)
+                continue
             t = symm_mem.empty(shape, dtype=torch.float32, device=self.dev)
             hdl = symm_mem.rendezvous(t, group.group_name)
             if not hdl.multicast_ptr:
                 raise RuntimeError("no multicast pointer")
             t.zero_()
-            self._symm[name] = (t, hdl, int(hdl.multicast_ptr))
+            entry = {"t": t, "hdl": hdl, "mc": int(hdl.multicast_ptr), "group": group.group_name, "busy": True}
+            if hit is None or not hit["busy"]:
+                _SYMM_CACHE[key] = entry          # (an entry in use by a live engine is left alone; this one is not cached)
+            self._symm[name] = (t, hdl, entry["mc"], entry)
         torch.cuda.synchronize(self.dev)
 
     def _rank_barrier(self):
@@ -393,16 +483,16 @@ class GammaEngine:
             self.item_pass(write_params)
 
     def close(self):
-        """Release the symmetric-memory tables (multi-GPU): state becomes ordinary device tensors.  Collective."""
+        """Detach from the symmetric-memory tables (multi-GPU): state becomes ordinary device tensors and the tables go
+        back to the cache for the next engine.  Every rank calls it at the same point of its program; no barrier is
+        needed: the last item pass ended with one (all remote stores into this replica have landed), the copy below is
+        stream-ordered, and the next engine's first remote store comes after a barrier that orders it behind this copy."""
         if self._symm:
-            import torch.distributed as dist
-            torch.cuda.synchronize(self.dev)
-            dist.barrier()
             self.E_beta = self._symm["E_beta"][0].clone()
             self.acc_item = None
+            for entry in self._symm.values():
+                entry[3]["busy"] = False
             self._symm = {}
-            torch.cuda.synchronize(self.dev)
-            dist.barrier()
         if self.exchange != "none":
             self.exchange = "closed"
 

@@ -13,7 +13,8 @@ from typing import Optional
 import numpy as np
 
 from . import _cabi
-from ._engine import EvalSet, GammaEngine, Trace, eval_stats, normalise_ids, predict, row_stride, table_to_host
+from ._engine import (DeviceLoop, EvalSet, GammaEngine, Trace, device_loop_enabled, eval_stats, eval_stats_launch,
+                      normalise_ids, predict, row_stride, table_to_host)
 from .poisson_mf_cavi import _DeviceBacked
 from .ratings import DEFAULT_SEG_LEN, DeviceRatings, to_device
 
@@ -158,7 +159,11 @@ class HPF_CAVI(_DeviceBacked):
         prev_val_rmse = None
         # the Gamma shape/rate tables are outputs only: they are written by the sweep that can be the last one
         params_every_sweep = self._track_elbo or (ev is not None and cfg.tol is not None)
-        for it in range(1, cfg.max_iter + 1):
+        host_iters = range(1, cfg.max_iter + 1)
+        if (device_loop_enabled() and not cfg.verbose and eng.world == 1 and self._allocation == "mean"
+                and not self._track_elbo and cfg.max_iter >= 1):
+            host_iters = self._fit_on_device(eng, ev, params_every_sweep)
+        for it in host_iters:
             if cfg.verbose:
                 print(f"\nHPF_CAVI iteration {it}/{cfg.max_iter}")
             if self._allocation == "digamma":
@@ -192,6 +197,28 @@ class HPF_CAVI(_DeviceBacked):
             self._init = None
         self._invalidate()
         return self
+
+    def _fit_on_device(self, eng, ev, params_every_sweep):
+        """The whole loop as one CUDA graph (DeviceLoop): no host round trip per iteration.  Returns the iterations that
+        are left for the host loop (the last sweep of a fit without early stopping, which alone writes the Gamma
+        parameters; everything if the driver cannot build the graph)."""
+        cfg = self.config
+        in_graph = cfg.max_iter if params_every_sweep else cfg.max_iter - 1
+        if in_graph >= 1:
+            try:
+                loop = DeviceLoop(eng.dev, in_graph, ev_out=None if ev is None else ev.out, rule=0, tol=cfg.tol)
+                with loop.body():
+                    eng.sweep(write_params=params_every_sweep)
+                    if ev is not None:
+                        eval_stats_launch(ev, eng.E_theta, eng.E_beta, self.n_users, self.n_items, eng.K, eng.ld)
+            except _cabi.PMFError as exc:
+                if exc.status != _cabi.PMF_EUNSUPPORTED:
+                    raise
+                return range(1, cfg.max_iter + 1)
+            self.n_iter_, hist = loop.run()
+            self.val_rmse_history_ = [float(v) for v in hist]
+            loop.free()
+        return range(in_graph + 1, cfg.max_iter + 1)
 
     def elbo(self, return_parts=False):
         """Evidence lower bound of the current variational state (observed-only HPF; parity unpinned)."""

@@ -30,11 +30,15 @@ DEFAULT_SEG_LEN = None  # None = auto_seg_len(nnz)
 
 
 def auto_seg_len(nnz):
-    """Longest run of observations one lane group handles alone.
+    """Longest run of observations one lane group handles alone, for ONE launch over `nnz` observations.
 
     Rows longer than this are cut into segments whose partial sums are combined by a second kernel.
-    Long segments are fine for throughput (segments are scheduled longest first); the cap only has to
-    keep enough independent segments for ~150 SMs x 64 groups: nnz/32768 clamped to [64, 1024].
+    Long segments are fine for throughput (segments are scheduled longest first), but a lane group walks its
+    segment 8 observations per memory round trip (~1 us under load), so the longest segment is the critical path
+    of the launch: 1024 observations ~ 0.1 ms.  nnz/32768 clamped to [64, 1024] keeps that below ~10 % of the launch
+    (26 ps per observation) and leaves enough independent segments for ~150 SMs x 64 groups.  Tiled / chunked
+    passes are several launches: the rule is applied to the observations of one launch (measured at 2 GPUs, 16 launches
+    per item pass: 3.05 ms with the whole shard's 1024, profiles/README.md).
     """
     want = (int(nnz) // 32768 + 7) // 8 * 8
     return max(64, min(1024, want))
@@ -191,7 +195,7 @@ class DeviceRatings:
     """
 
     def __init__(self, u, i, x, n_users, n_items, device=None, seg_len=DEFAULT_SEG_LEN, shard=None, row_bytes=None,
-                 tile_bytes=None, user_pass_tiles=None, item_pass_tiles=None, shard_input="full"):
+                 tile_bytes=None, user_pass_tiles=None, item_pass_tiles=None, shard_input="full", item_chunks=None):
         _cabi.require_cuda()
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.device = device
@@ -213,26 +217,33 @@ class DeviceRatings:
             self.user_bounds = np.array([0, self.n_users], dtype=np.int64)
         self.nnz_local = u_d.numel()
         self.user_lo, self.user_hi = int(self.user_bounds[self.rank]), int(self.user_bounds[self.rank + 1])
-        if seg_len is None:
-            seg_len = auto_seg_len(self.nnz_local)
-        self.seg_len = seg_len
+        # several GPUs: the item rows are processed in chunks so that the cross-rank combine of one chunk overlaps the pass
+        # over the next (GammaEngine.item_pass); the number is fixed here because it sets the size of a launch
+        if item_chunks is None:
+            item_chunks = int(os.environ.get("PMF_ITEM_CHUNKS", 4)) if self.world > 1 else 1
+        self.item_chunks = max(1, min(int(item_chunks), self.n_items)) if self.world > 1 else 1
         n_own = self.user_hi - self.user_lo
         env = lambda k: int(os.environ[k]) if os.environ.get(k) else None
         self.item_tile_bounds = tile_bounds(0, self.n_items, row_bytes, tile_bytes,
                                             user_pass_tiles if user_pass_tiles is not None else env("PMF_USER_PASS_TILES"))
         self.user_tile_bounds = tile_bounds(self.user_lo, self.user_hi, row_bytes, tile_bytes,
                                             item_pass_tiles if item_pass_tiles is not None else env("PMF_ITEM_PASS_TILES"))
+        launches_u = len(self.item_tile_bounds) - 1
+        launches_i = (len(self.user_tile_bounds) - 1) * self.item_chunks
+        self.seg_len_user = seg_len if seg_len is not None else auto_seg_len(self.nnz_local // launches_u)
+        self.seg_len_item = seg_len if seg_len is not None else auto_seg_len(self.nnz_local // launches_i)
+        self.seg_len = self.seg_len_user
         with torch.cuda.device(device):
             u_loc = u_d - self.user_lo if self.user_lo else u_d     # rows of the user pass are local to the rank's range
             self.user_tiles = self._build_tiles(u_loc, i_d, x_d, self.item_tile_bounds, by_item=True, key_is_user=True,
-                                                n_rows=n_own, row_offset=self.user_lo) if n_own > 0 else []
+                                                n_rows=n_own, row_offset=self.user_lo, seg_len=self.seg_len_user) if n_own > 0 else []
             del u_loc                                               # columns of the item pass are global user ids
             self.item_tiles = self._build_tiles(u_d, i_d, x_d, self.user_tile_bounds, by_item=False, key_is_user=False,
-                                                n_rows=self.n_items, row_offset=0)
+                                                n_rows=self.n_items, row_offset=0, seg_len=self.seg_len_item)
         del u_d, i_d, x_d
 
     # -- construction helpers -------------------------------------------------------------------
-    def _build_tiles(self, u_d, i_d, x_d, bounds, by_item, key_is_user, n_rows, row_offset):
+    def _build_tiles(self, u_d, i_d, x_d, bounds, by_item, key_is_user, n_rows, row_offset, seg_len):
         """One Grouped per tile of `bounds` (ranges of the OTHER side's ids); the key side is grouped."""
         T = len(bounds) - 1
         if T > 1:
@@ -243,7 +254,7 @@ class DeviceRatings:
         for t in range(T):
             a, b = int(offs[t]), int(offs[t + 1])
             key, other = (u_p[a:b], i_p[a:b]) if key_is_user else (i_p[a:b], u_p[a:b])
-            tiles.append(Grouped.build(key, other, x_p[a:b], n_rows, self.seg_len, row_offset))
+            tiles.append(Grouped.build(key, other, x_p[a:b], n_rows, seg_len, row_offset))
         return tiles
 
     def _route_to_owner(self, u_h, i_h, x_h, shard_input):

@@ -46,7 +46,7 @@ for combo in combos:
     torch.cuda.synchronize()
     tu_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev])); ti_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     print(f"TILES {name} {combo}{':' + tune if tune else ''}: user pass {tu_ms:.3f} ms, item pass {ti_ms:.3f} ms, sweep {tu_ms + ti_ms:.3f} ms "
-          f"-> {w.nnz / (tu_ms + ti_ms) * 1e3:.3e} nnz*it/s (seg_len {dr.seg_len}, launches {eng.launches_per_sweep})", flush=True)
+          f"-> {w.nnz / (tu_ms + ti_ms) * 1e3:.3e} nnz*it/s (seg_len {dr.seg_len_user}/{dr.seg_len_item}, launches {eng.launches_per_sweep})", flush=True)
     for kv in filter(None, tune.split("+")):
         _cabi.call("pmf_tune", kv.split("=")[0].encode(), -1 if "chunk_reduce" in kv else 0)
     dr.free()

@@ -74,8 +74,7 @@ def main():
     # B: forced tiles + pipelined chunks
     mb = hpf(T)
     mb.n_users, mb.n_items = N, M
-    mb._ratings_kw = dict(user_pass_tiles=2, item_pass_tiles=3)
-    mb._engine_kw = dict(item_chunks=3)
+    mb._ratings_kw = dict(user_pass_tiles=2, item_pass_tiles=3, item_chunks=3)
     mb.fit_arrays(u, i, x, init)
     report["B"] = max(rel_max(getattr(mb, k), ref[k]) for k in HPF_TABLES)
     same = same and replicas_identical(mb, world)

@@ -187,3 +187,25 @@ def test_count_keys():
     assert np.array_equal(counts.cpu().numpy(), np.bincount(u, minlength=7000))
     with pytest.raises(_cabi.PMFError):
         _cabi.call("pmf_count_keys", ud.data_ptr(), ud.numel(), 6999, counts.data_ptr(), _cabi.stream_ptr())
+
+
+@pytest.mark.parametrize("tol", [None, 2e-3])
+def test_device_loop_equals_host_loop(tol, monkeypatch):
+    """f2: the fit loop as one CUDA graph with a device-side WHILE (sweeps + validation statistics + the reference's
+    stopping rule, hpf_cavi.py:196-211) stops at the same iteration, with the same RMSE history and bit-identical
+    factors as the host loop that reads the statistics back after every sweep."""
+    from prob_matrix_factorization_b200 import synth
+    from prob_matrix_factorization_b200.hpf_cavi import HPF_CAVI, HPF_CAVI_Config
+    N, M, nnz, K = 3000, 2000, 40_000, 12
+    (u, i, x), (vu, vi, vx), _ = synth.make_splits(N, M, nnz, seed=11)
+    hp = dict(a=0.3, a_prime=5.0, b_prime=5.0, c=0.3, c_prime=5.0, d_prime=5.0)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PMF_DEVICE_LOOP", mode)
+        m = HPF_CAVI(HPF_CAVI_Config(n_factors=K, max_iter=25, tol=tol, random_state=3, verbose=False, **hp))
+        m.fit(frame(u, i, x + 1.0), frame(vu, vi, vx + 1.0))
+        out[mode] = (m.n_iter_, np.array(m.val_rmse_history_), m.E_theta, m.gamma_b_beta, m.E_eta)
+    assert out["1"][0] == out["0"][0] and (tol is None or 2 <= out["1"][0] < 25)
+    assert np.array_equal(out["1"][1], out["0"][1]) and len(out["1"][1]) == out["1"][0]
+    for a, b in zip(out["1"][2:], out["0"][2:]):
+        assert np.array_equal(a, b)
