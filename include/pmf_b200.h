@@ -226,12 +226,17 @@ int pmf_predict(const int32_t* d_users, const int32_t* d_items, int64_t n,
  * d_out (float64, zeroed by the call) layout:
  *   [0] count  [1] sum (y-p)^2  [2] sum |y-p|  [3] sum y*log(max(p,1e-10)) - p - lgamma(y+1)
  *   [4 .. 4+n_labels) per-label sum |y-p|   [4+n_labels .. 4+2 n_labels) per-label count
- * (global_mean shifts y_true and the prediction alike, so it cancels in every statistic but [3].) */
+ * (global_mean shifts y_true and the prediction alike, so it cancels in every statistic but [3].)
+ * GaussianLogPredictiveLikelihood (metrics.py:18-35, called with the factor means only: no biases, global_mean 0) follows
+ * from [0] and [1]:  -0.5 [0] log(2 pi s^2) - [1] / (2 s^2)  with s^2 = sigma^2 (the reference squares its `sigma` argument).
+ * The reduction is deterministic (bit-identical results for identical inputs: the early-stopping rule compares them).
+ * d_scratch: pmf_eval_stats_scratch_bytes() bytes of device memory, 8-byte aligned, private to the call's stream. */
+int64_t pmf_eval_stats_scratch_bytes(void);
 int pmf_eval_stats(const int32_t* d_users, const int32_t* d_items, const float* d_y,
                    const int32_t* d_label, int32_t n_labels, int64_t n,
                    const float* d_F_user, int32_t n_users, const float* d_F_item, int32_t n_items,
                    int32_t K, int32_t ld, const float* d_b_user, const float* d_b_item,
-                   float global_mean, int32_t drop_invalid, double* d_out, void* stream);
+                   float global_mean, int32_t drop_invalid, double* d_out, void* d_scratch, void* stream);
 
 /* ---- f2: device-side training loop (sweeps + validation + early stopping as one CUDA graph) -----------------------
  * Replaces the per-iteration host decision of hpf_cavi.py:196-211 / poisson_mf_cavi.py:200-217 /

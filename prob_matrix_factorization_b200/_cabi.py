@@ -106,8 +106,9 @@ _PROTOTYPES = {
     "pmf_hpf_map_predict": (C.c_int, [VP, VP, C.c_int32, C.c_int64, VP, VP, C.c_int32, C.c_int32, C.c_int32, VP, VP]),
     "pmf_predict": (C.c_int, [VP, VP, C.c_int64, VP, C.c_int32, VP, C.c_int32, C.c_int32, C.c_int32,
                               VP, VP, C.c_float, C.c_int32, VP, VP]),
+    "pmf_eval_stats_scratch_bytes": (C.c_int64, []),
     "pmf_eval_stats": (C.c_int, [VP, VP, VP, VP, C.c_int32, C.c_int64, VP, C.c_int32, VP, C.c_int32,
-                                 C.c_int32, C.c_int32, VP, VP, C.c_float, C.c_int32, VP, VP]),
+                                 C.c_int32, C.c_int32, VP, VP, C.c_float, C.c_int32, VP, VP, VP]),
 }
 
 

@@ -119,6 +119,7 @@ class EvalSet:
         else:
             self.label, self.n_labels = None, 0
         self.out = torch.zeros(4 + 2 * MAX_DEVICE_LABELS, dtype=torch.float64, device=device)
+        self.scratch = torch.zeros((int(_cabi.load().pmf_eval_stats_scratch_bytes()) + 7) // 8, dtype=torch.int64, device=device)
 
 
 def eval_stats_launch(ev, F_user, F_item, n_users, n_items, K, ld, b_user=None, b_item=None, global_mean=0.0):
@@ -127,7 +128,7 @@ def eval_stats_launch(ev, F_user, F_item, n_users, n_items, K, ld, b_user=None, 
         _cabi.call("pmf_eval_stats", ev.u.data_ptr(), ev.i.data_ptr(), ev.y.data_ptr(), _cabi.ptr(ev.label),
                    ev.n_labels, ev.n, F_user.data_ptr(), n_users, F_item.data_ptr(), n_items, K, ld,
                    _cabi.ptr(b_user), _cabi.ptr(b_item), float(global_mean), int(ev.drop_invalid),
-                   ev.out.data_ptr(), _cabi.stream_ptr())
+                   ev.out.data_ptr(), ev.scratch.data_ptr(), _cabi.stream_ptr())
 
 
 class DeviceLoop:
@@ -205,7 +206,7 @@ def eval_stats(ev, F_user, F_item, n_users, n_items, K, ld, b_user=None, b_item=
             dist.all_reduce(ev.out)                          # float64 sums over the ranks' rows: identical everywhere
         out = ev.out.cpu().numpy()
     cnt = out[0]
-    res = {"count": cnt, "rmse": float(np.sqrt(out[1] / cnt)) if cnt > 0 else float("nan"),
+    res = {"count": cnt, "sse": float(out[1]), "rmse": float(np.sqrt(out[1] / cnt)) if cnt > 0 else float("nan"),
            "mae": float(out[2] / cnt) if cnt > 0 else float("nan"), "poisson_lpl": float(out[3])}
     if ev.on_device:
         sae, c = out[4:4 + ev.n_labels], out[4 + ev.n_labels:4 + 2 * ev.n_labels]

@@ -8,6 +8,8 @@
 //
 // HBM-bound gathers: 8 lanes per (user,item) pair, 128-bit loads, float64 accumulation (cheap; the
 // factor rows are float32).
+#include <stddef.h>
+
 #include "common.cuh"
 
 namespace pmf {
@@ -67,13 +69,27 @@ __global__ void __launch_bounds__(256) predict_kernel(const PredictArgs a, doubl
     }
 }
 
+// Scratch of pmf_eval_stats: per-block partial sums of the four scalars, fixed-point per-label |error| sums, a counter.
+constexpr int kEvalMaxBlocks = kNumSMs * 8;
+struct EvalScratch {
+    double part[kEvalMaxBlocks][4];
+    unsigned long long lab_abs[kMaxLabels];   // sum |y - p| * 2^32, rounded per term
+    unsigned long long lab_cnt[kMaxLabels];
+    unsigned int done;
+};
+constexpr double kLabScale = 4294967296.0;    // 2^32
+
+// DETERMINISTIC reduction (the early-stopping rule compares RMSEs of consecutive sweeps against a tolerance, on the host or
+// -- pmf_loop_decide -- on the device, and sharded fits must take the same decision on every rank): the element -> thread
+// mapping is fixed, warp and block sums use fixed trees, every block parks its four sums in scratch and the LAST block to
+// finish adds them in block order; per-label sums are integer atomics (counts, and |error| in 2^-32 fixed point), whose
+// result does not depend on the order of arrival.
 __global__ void __launch_bounds__(256) eval_stats_kernel(const PredictArgs a, const float* __restrict__ y,
                                                          const int32_t* __restrict__ label, int n_labels,
-                                                         int drop_invalid, double* __restrict__ out) {
-    __shared__ double s_lab[2 * kMaxLabels];
+                                                         int drop_invalid, double* __restrict__ out,
+                                                         EvalScratch* __restrict__ sc) {
     __shared__ double s_red[4][8];
-    for (int k = threadIdx.x; k < 2 * kMaxLabels; k += blockDim.x) s_lab[k] = 0.0;
-    __syncthreads();
+    __shared__ bool s_last;
     const int gl = threadIdx.x & (kEvalGroup - 1);
     const int64_t groups = (int64_t)gridDim.x * blockDim.x / kEvalGroup;
     const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kEvalGroup;
@@ -95,13 +111,13 @@ __global__ void __launch_bounds__(256) eval_stats_kernel(const PredictArgs a, co
             if (label) {
                 const int lb = label[t];
                 if (lb >= 0 && lb < n_labels) {
-                    atomicAdd(&s_lab[lb], fabs(e));
-                    atomicAdd(&s_lab[kMaxLabels + lb], 1.0);
+                    atomicAdd(&sc->lab_abs[lb], (unsigned long long)llrint(fmin(fabs(e), 1048576.0) * kLabScale));
+                    atomicAdd(&sc->lab_cnt[lb], 1ull);
                 }
             }
         }
     }
-    // block reduction of the four scalars
+    // block reduction of the four scalars (fixed shuffle tree, then warps in order)
     double v[4] = {cnt, sse, sae, lpl};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -114,14 +130,24 @@ __global__ void __launch_bounds__(256) eval_stats_kernel(const PredictArgs a, co
     if (threadIdx.x < 4) {
         double t = 0;
         for (int w = 0; w < 8; ++w) t += s_red[threadIdx.x][w];
-        atomicAdd(out + threadIdx.x, t);
+        sc->part[blockIdx.x][threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&sc->done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < 4) {
+        double t = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += sc->part[b][threadIdx.x];
+        out[threadIdx.x] = t;
     }
     for (int k = threadIdx.x; k < n_labels; k += blockDim.x) {
-        if (s_lab[kMaxLabels + k] != 0.0) {
-            atomicAdd(out + 4 + k, s_lab[k]);
-            atomicAdd(out + 4 + n_labels + k, s_lab[kMaxLabels + k]);
-        }
+        out[4 + k] = (double)sc->lab_abs[k] / kLabScale;
+        out[4 + n_labels + k] = (double)sc->lab_cnt[k];
     }
+    if (threadIdx.x == 0) sc->done = 0;
 }
 
 static int fill_args(PredictArgs& a, const int32_t* d_users, const int32_t* d_items, int64_t n, const float* d_F_user,
@@ -142,7 +168,7 @@ static unsigned eval_grid(int64_t n) {
     const int64_t per_block = 256 / kEvalGroup;
     int64_t blocks = cdiv(n > 0 ? n : 1, per_block);
     const int64_t cap = (int64_t)kNumSMs * 8;
-    return (unsigned)(blocks < cap ? blocks : cap);
+    return (unsigned)(blocks < cap ? blocks : cap);   // <= kEvalMaxBlocks
 }
 
 __global__ void scale_rows_kernel(const float* __restrict__ F, const float* __restrict__ scale, int64_t n4, int ld4,
@@ -174,20 +200,25 @@ int pmf_predict(const int32_t* d_users, const int32_t* d_items, int64_t n, const
     return PMF_OK;
 }
 
+int64_t pmf_eval_stats_scratch_bytes(void) { return (int64_t)sizeof(EvalScratch); }
+
 int pmf_eval_stats(const int32_t* d_users, const int32_t* d_items, const float* d_y, const int32_t* d_label,
                    int32_t n_labels, int64_t n, const float* d_F_user, int32_t n_users, const float* d_F_item,
                    int32_t n_items, int32_t K, int32_t ld, const float* d_b_user, const float* d_b_item,
-                   float global_mean, int32_t drop_invalid, double* d_out, void* stream) {
+                   float global_mean, int32_t drop_invalid, double* d_out, void* d_scratch, void* stream) {
     PredictArgs a;
     PMF_TRY(fill_args(a, d_users, d_items, n, d_F_user, n_users, d_F_item, n_items, K, ld, d_b_user, d_b_item,
                       global_mean, 0));
     PMF_REQUIRE(d_out != nullptr, "d_out is NULL");
     PMF_REQUIRE(n_labels >= 0 && n_labels <= kMaxLabels, "n_labels=%d exceeds %d", n_labels, kMaxLabels);
     PMF_REQUIRE(n == 0 || d_y, "d_y is NULL");
+    PMF_REQUIRE(n == 0 || (d_scratch != nullptr && ((uintptr_t)d_scratch & 7) == 0), "d_scratch is NULL or misaligned");
     cudaStream_t s = (cudaStream_t)stream;
     PMF_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * (4 + 2 * (size_t)n_labels), s));
     if (n == 0) return PMF_OK;
-    eval_stats_kernel<<<eval_grid(n), 256, 0, s>>>(a, d_y, n_labels > 0 ? d_label : nullptr, n_labels, drop_invalid, d_out);
+    EvalScratch* sc = (EvalScratch*)d_scratch;
+    PMF_CUDA(cudaMemsetAsync(sc->lab_abs, 0, sizeof(EvalScratch) - offsetof(EvalScratch, lab_abs), s));
+    eval_stats_kernel<<<eval_grid(n), 256, 0, s>>>(a, d_y, n_labels > 0 ? d_label : nullptr, n_labels, drop_invalid, d_out, sc);
     PMF_LAUNCH_CHECK();
     return PMF_OK;
 }

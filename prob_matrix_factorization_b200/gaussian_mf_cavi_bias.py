@@ -241,3 +241,20 @@ class GaussianMFCAVI(_DeviceBacked):
     def evaluate_macro_mae(self, df, global_mean):
         st = self._frame_eval(df, global_mean)
         return np.nan if st["count"] == 0 else st["macro_mae"]
+
+    def log_predictive_likelihood(self, df, sigma=None):
+        """``GaussianLogPredictiveLikelihood(df, m_theta, m_beta, sigma)`` (metrics.py:18-35) evaluated on the device.
+
+        As the reference's callers use it (run_gaussian_mf_best_k.py:54): predictions are the factor means' dot product
+        only (no biases, no global mean), ``sigma`` defaults to ``config.sigma2`` and is SQUARED by the function
+        although it already is a variance (metrics.py:33).  Rows with unseen ids (an IndexError in the reference) are
+        dropped."""
+        e = self._engine
+        if e is None:
+            raise RuntimeError("fit() must be called before log_predictive_likelihood()")
+        sigma = self.config.sigma2 if sigma is None else sigma
+        ev = EvalSet(df["u"].to_numpy(), df["i"].to_numpy(), df["rating"].to_numpy(dtype=float), self.n_users,
+                     self.n_items, e.dev, drop_invalid=True)
+        st = eval_stats(ev, e.m_theta, e.m_beta, self.n_users, self.n_items, e.K, e.ld)
+        variance = float(sigma) ** 2
+        return float(-0.5 * st["count"] * np.log(2 * np.pi * variance) - st["sse"] / (2 * variance))

@@ -30,6 +30,12 @@ def test_gaussian_bias_golden(golden):
     assert abs(m.evaluate_macro_mae(val, g["global_mean"]) - g["val_macro_mae"]) < TOL * g["val_macro_mae"]
     test = frame(g["test_u"], g["test_i"], g["test_x"])
     assert abs(m.evaluate_rmse(test, g["global_mean"]) - g["test_rmse"]) < TOL * g["test_rmse"]
+    # GaussianLogPredictiveLikelihood (metrics.py:18-35; the golden value was computed by the reference's function on the
+    # rows with seen ids, with sigma2 passed as `sigma` as the reference's scripts do) -- device path and host function
+    from prob_matrix_factorization_b200 import metrics
+    assert abs(m.log_predictive_likelihood(test) - g["test_lpl"]) < TOL * abs(g["test_lpl"])
+    seen = test[(test.u < m.n_users) & (test.i < m.n_items)]
+    assert abs(metrics.GaussianLogPredictiveLikelihood(seen, m.m_theta, m.m_beta, g["sigma2"]) - g["test_lpl"]) < TOL * abs(g["test_lpl"])
     # early stopping needs 0 <= improvement < tol (gaussian_mf_cavi_bias.py:279)
     cfg2 = GaussianMFCAVIConfig(n_factors=g["K"], sigma2=g["sigma2"], eta_theta2=g["eta_theta2"], eta_beta2=g["eta_beta2"],
                                 eta_bias2=g["eta_bias2"], max_iter=g["es_max_iter"], tol=g["es_tol"],
