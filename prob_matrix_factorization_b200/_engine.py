@@ -131,6 +131,19 @@ def eval_stats_launch(ev, F_user, F_item, n_users, n_items, K, ld, b_user=None, 
                    ev.out.data_ptr(), ev.scratch.data_ptr(), _cabi.stream_ptr())
 
 
+_SIDE_STREAMS = {}
+
+
+def side_stream(dev, which="loop"):
+    """One long-lived non-default stream per (device, purpose): creating a stream costs 25-900 ms on a cold context
+    (measured inside fits, profiles/README.md), far more than a small fit."""
+    dev = torch.device(dev)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), which)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 class DeviceLoop:
     """The fit loop as one CUDA graph with a device-side WHILE (pmf_loop_*, csrc/loop.cu): sweeps, validation statistics
     and the reference's early-stopping rule run back to back on the GPU; the host reads the iteration count and the
@@ -146,7 +159,7 @@ class DeviceLoop:
         self.dev = torch.device(dev)
         self.max_iter = int(max_iter)
         self.ev_out, self.rule, self.tol = ev_out, int(rule), tol
-        self.stream = torch.cuda.Stream(device=self.dev)
+        self.stream = side_stream(self.dev, "loop")
         self.iter = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.history = torch.zeros(max(1, self.max_iter), dtype=torch.float64, device=self.dev)
         self._h = C.c_void_p()
@@ -302,7 +315,7 @@ class GammaEngine:
         n_item_tiles = len(ratings.item_tiles)
         if self.exchange == "mc":
             self.E_beta, self.acc_item = self._symm["E_beta"][0], self._symm["acc_item"][0]
-            self._side = torch.cuda.Stream(device=self.dev)
+            self._side = side_stream(self.dev, "combine")
         else:
             self.E_beta = f(self.M)
             self.acc_item = f(self.M, 2 * self.ld) if (self.world > 1 or n_item_tiles > 1) else None

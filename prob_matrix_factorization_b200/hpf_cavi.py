@@ -205,8 +205,10 @@ class HPF_CAVI(_DeviceBacked):
         cfg = self.config
         in_graph = cfg.max_iter if params_every_sweep else cfg.max_iter - 1
         if in_graph >= 1:
+            tr = Trace()
             try:
                 loop = DeviceLoop(eng.dev, in_graph, ev_out=None if ev is None else ev.out, rule=0, tol=cfg.tol)
+                tr.mark("device loop: construct")
                 with loop.body():
                     eng.sweep(write_params=params_every_sweep)
                     if ev is not None:
@@ -215,9 +217,12 @@ class HPF_CAVI(_DeviceBacked):
                 if exc.status != _cabi.PMF_EUNSUPPORTED:
                     raise
                 return range(1, cfg.max_iter + 1)
+            tr.mark("device loop: capture + instantiate")
             self.n_iter_, hist = loop.run()
+            tr.mark(f"device loop: run ({self.n_iter_} iterations)")
             self.val_rmse_history_ = [float(v) for v in hist]
             loop.free()
+            tr.mark("device loop: free")
         return range(in_graph + 1, cfg.max_iter + 1)
 
     def elbo(self, return_parts=False):
