@@ -302,17 +302,19 @@ int pmf_hpf_map_loss_grad(const void* d_users, const void* d_items, int32_t id_b
 int pmf_adam_dense_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
                         float beta1, float beta2, float eps, float step_size, float bias_correction2_sqrt,
                         void* stream);
-/* Lazy ("touch-only") Adam, exactly equivalent to the dense update: rows without gradient are replayed in
- * registers when next touched.  All arrays are device memory owned by the caller:
- * parameters, first/second moments and dense gradient scratch for theta (N,K), beta (M,K), xi (N), eta (M);
- * last_* / claim_* int32 per row (zero-initialised: "up to date with step 0"); touched_* int32[batch];
- * counters int32[2]; step_size[s] = lr/(1-beta1^s) and bc2_sqrt[s] = sqrt(1-beta2^s) for every step s (1-based). */
+/* Lazy ("touch-only") Adam, equivalent to the dense update: a row without gradient in a step is not touched; the
+ * zero-gradient steps it skipped are applied (in closed form) when it is next referenced, together with its deferred
+ * last real step.  All arrays are device memory owned by the caller: parameters, first/second
+ * moments and gradient accumulators for theta (N,K), beta (M,K), xi (N), eta (M); last_* / claim_* int32 per row,
+ * zero-initialised (last = s > 0: up to date with step s-1, the gradient of step s is accumulated but not applied;
+ * last = -s <= 0: up to date with step s); step_size[s] = lr/(1-beta1^s) and bc2_sqrt[s] = sqrt(1-beta2^s) for every
+ * step s (1-based). */
 typedef struct pmf_lazy_adam {
     float *theta, *beta, *xi, *eta;
     float *m_theta, *m_beta, *m_xi, *m_eta;
     float *v_theta, *v_beta, *v_xi, *v_eta;
     float *g_theta, *g_beta, *g_xi, *g_eta;
-    int32_t *last_user, *last_item, *claim_user, *claim_item, *touched_user, *touched_item, *counters;
+    int32_t *last_user, *last_item, *claim_user, *claim_item;
     const float *step_size, *bc2_sqrt;
     float beta1, beta2, eps;
     /* Closed-form catch-up (both or neither; NULL = replay skipped steps one by one).  float64, indexed by step like
@@ -323,8 +325,9 @@ typedef struct pmf_lazy_adam {
      * ratio^J tail[s+J], and decays m, v by beta^J (first order in eps/sqrt(v); runs where that exceeds 1e-3 are replayed). */
     const double *tail1, *tail2;
 } pmf_lazy_adam;
-/* One pass over n (already shuffled) ratings in mini-batches of `batch`: per step catch the batch's rows up,
- * fused loss+gradient, Adam step on the touched rows.  step0 = steps taken so far; adds the losses to *d_loss. */
+/* One pass over n (already shuffled) ratings in mini-batches of `batch`, ONE kernel per step: the first lane group to
+ * reference a row settles it (deferred Adam step + catch-up, gradient zeroed), the others wait for it, then every
+ * group adds its element's loss and gradients.  step0 = steps taken so far; adds the losses to *d_loss. */
 int pmf_hpf_map_lazy_epoch(const pmf_lazy_adam* st, const void* d_users, const void* d_items, int32_t id_bytes,
                            const float* d_ratings, int64_t n, int64_t batch, int64_t step0, const float* d_user_scale,
                            const float* d_item_scale, int32_t N, int32_t M, int32_t K, float a, float a_prime,

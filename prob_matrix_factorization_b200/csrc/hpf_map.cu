@@ -28,10 +28,87 @@ struct MapArgs {
     int32_t* bad;
 };
 
-// One group of G lanes per batch element; lane l owns factors k = l, l+G, ...
+// Loss terms and gradients of ONE batch element (u, it, r), computed by the G lanes of a group (lane l owns factors
+// k = l, l+G, ...); gradients are added to the dense gradient tensors with float atomics (duplicate ids in a batch).
+// Returns the element's loss (valid in lane 0 of the group).
+template <int G>
+__device__ __forceinline__ double map_element(const MapArgs& a, int64_t u, int64_t it, float r, int gl, unsigned gmask) {
+    constexpr int MAXV = 8;   // K <= G * MAXV
+    const float s = a.user_scale[u], t = a.item_scale[it];
+    const float* tr = a.theta + (size_t)u * a.K;
+    const float* br = a.beta + (size_t)it * a.K;
+    float th[MAXV], be[MAXV], traw[MAXV], braw[MAXV];
+    float dot = 0.f, sum_th = 0.f, sum_be = 0.f, sum_lth = 0.f, sum_lbe = 0.f;
+#pragma unroll
+    for (int v = 0; v < MAXV; ++v) {
+        const int k = gl + v * G;
+        if (k < a.K) {
+            traw[v] = __ldcg(tr + k); braw[v] = __ldcg(br + k);   // L2: rows may have been settled by another SM in this kernel
+            th[v] = softplus_t(traw[v]); be[v] = softplus_t(braw[v]);
+            dot = fmaf(th[v], be[v], dot);
+            sum_th += th[v]; sum_be += be[v];
+            sum_lth += logf(th[v]); sum_lbe += logf(be[v]);
+        }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        dot += __shfl_xor_sync(gmask, dot, o);
+        sum_th += __shfl_xor_sync(gmask, sum_th, o);
+        sum_be += __shfl_xor_sync(gmask, sum_be, o);
+        sum_lth += __shfl_xor_sync(gmask, sum_lth, o);
+        sum_lbe += __shfl_xor_sync(gmask, sum_lbe, o);
+    }
+    const float xr = __ldcg(a.xi + u), er = __ldcg(a.eta + it);
+    const float xi = softplus_t(xr), eta = softplus_t(er);
+    const float lam = fmaxf(dot, 1e-6f);                         // hpf_pytorch.py:80
+    const float g = dot >= 1e-6f ? 1.f - r / lam : 0.f;          // clamp passes gradient only inside its range
+#pragma unroll
+    for (int v = 0; v < MAXV; ++v) {
+        const int k = gl + v * G;
+        if (k < a.K) {
+            const float dth = g * be[v] + s * (xi - (a.a - 1.f) / th[v]);
+            const float dbe = g * th[v] + t * (eta - (a.c - 1.f) / be[v]);
+            atomicAdd(a.g_theta + (size_t)u * a.K + k, dth * softplus_grad_t(traw[v]));
+            atomicAdd(a.g_beta + (size_t)it * a.K + k, dbe * softplus_grad_t(braw[v]));
+        }
+    }
+    double loss = 0.0;
+    if (gl == 0) {
+        const float Kf = (float)a.K;
+        const float lxi = logf(xi), leta = logf(eta);
+        const float dxi = s * (-Kf * a.a / xi + sum_th - (a.a_prime - 1.f) / xi + a.b_prime);
+        const float deta = t * (-Kf * a.c / eta + sum_be - (a.c_prime - 1.f) / eta + a.d_prime);
+        atomicAdd(a.g_xi + u, dxi * softplus_grad_t(xr));
+        atomicAdd(a.g_eta + it, deta * softplus_grad_t(er));
+        // loss terms (hpf_pytorch.py:83, :145-152, :158-165, :169-173, :176-180)
+        const float nll = lam - r * logf(lam);
+        const float p_th = s * (-a.a * Kf * lxi + xi * sum_th - (a.a - 1.f) * sum_lth);
+        const float p_be = t * (-a.c * Kf * leta + eta * sum_be - (a.c - 1.f) * sum_lbe);
+        const float p_xi = s * (-(a.a_prime - 1.f) * lxi + a.b_prime * xi);
+        const float p_eta = t * (-(a.c_prime - 1.f) * leta + a.d_prime * eta);
+        loss = (double)nll + (double)p_th + (double)p_be + (double)p_xi + (double)p_eta;
+    }
+    return loss;
+}
+
+// block reduction of the loss -> one float64 atomic per block
+__device__ __forceinline__ void block_add_loss(double loss, double* out) {
+    __shared__ double s_red[8];
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    if (lane == 0) s_red[threadIdx.x >> 5] = loss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[w];
+        atomicAdd(out, tot);
+    }
+}
+
+// One group of G lanes per batch element.
 template <int G, typename IdT>
 __global__ void __launch_bounds__(256) hpf_map_loss_grad_kernel(const MapArgs a) {
-    constexpr int MAXV = 8;   // K <= G * MAXV
     const int lane = threadIdx.x & 31, gl = lane & (G - 1);
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -41,73 +118,10 @@ __global__ void __launch_bounds__(256) hpf_map_loss_grad_kernel(const MapArgs a)
         if (u < 0 || u >= a.N || it < 0 || it >= a.M) {
             if (gl == 0) atomicOr(a.bad, 1);   // torch indexing would raise IndexError
         } else {
-            const float r = a.ratings[gid];
-            const float s = a.user_scale[u], t = a.item_scale[it];
-            const float* tr = a.theta + (size_t)u * a.K;
-            const float* br = a.beta + (size_t)it * a.K;
-            float th[MAXV], be[MAXV], traw[MAXV], braw[MAXV];
-            float dot = 0.f, sum_th = 0.f, sum_be = 0.f, sum_lth = 0.f, sum_lbe = 0.f;
-#pragma unroll
-            for (int v = 0; v < MAXV; ++v) {
-                const int k = gl + v * G;
-                if (k < a.K) {
-                    traw[v] = tr[k]; braw[v] = br[k];
-                    th[v] = softplus_t(traw[v]); be[v] = softplus_t(braw[v]);
-                    dot = fmaf(th[v], be[v], dot);
-                    sum_th += th[v]; sum_be += be[v];
-                    sum_lth += logf(th[v]); sum_lbe += logf(be[v]);
-                }
-            }
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) {
-                dot += __shfl_xor_sync(gmask, dot, o);
-                sum_th += __shfl_xor_sync(gmask, sum_th, o);
-                sum_be += __shfl_xor_sync(gmask, sum_be, o);
-                sum_lth += __shfl_xor_sync(gmask, sum_lth, o);
-                sum_lbe += __shfl_xor_sync(gmask, sum_lbe, o);
-            }
-            const float xr = a.xi[u], er = a.eta[it];
-            const float xi = softplus_t(xr), eta = softplus_t(er);
-            const float lam = fmaxf(dot, 1e-6f);                         // hpf_pytorch.py:80
-            const float g = dot >= 1e-6f ? 1.f - r / lam : 0.f;          // clamp passes gradient only inside its range
-#pragma unroll
-            for (int v = 0; v < MAXV; ++v) {
-                const int k = gl + v * G;
-                if (k < a.K) {
-                    const float dth = g * be[v] + s * (xi - (a.a - 1.f) / th[v]);
-                    const float dbe = g * th[v] + t * (eta - (a.c - 1.f) / be[v]);
-                    atomicAdd(a.g_theta + (size_t)u * a.K + k, dth * softplus_grad_t(traw[v]));
-                    atomicAdd(a.g_beta + (size_t)it * a.K + k, dbe * softplus_grad_t(braw[v]));
-                }
-            }
-            if (gl == 0) {
-                const float Kf = (float)a.K;
-                const float lxi = logf(xi), leta = logf(eta);
-                const float dxi = s * (-Kf * a.a / xi + sum_th - (a.a_prime - 1.f) / xi + a.b_prime);
-                const float deta = t * (-Kf * a.c / eta + sum_be - (a.c_prime - 1.f) / eta + a.d_prime);
-                atomicAdd(a.g_xi + u, dxi * softplus_grad_t(xr));
-                atomicAdd(a.g_eta + it, deta * softplus_grad_t(er));
-                // loss terms (hpf_pytorch.py:83, :145-152, :158-165, :169-173, :176-180)
-                const float nll = lam - r * logf(lam);
-                const float p_th = s * (-a.a * Kf * lxi + xi * sum_th - (a.a - 1.f) * sum_lth);
-                const float p_be = t * (-a.c * Kf * leta + eta * sum_be - (a.c - 1.f) * sum_lbe);
-                const float p_xi = s * (-(a.a_prime - 1.f) * lxi + a.b_prime * xi);
-                const float p_eta = t * (-(a.c_prime - 1.f) * leta + a.d_prime * eta);
-                loss = (double)nll + (double)p_th + (double)p_be + (double)p_xi + (double)p_eta;
-            }
+            loss = map_element<G>(a, u, it, a.ratings[gid], gl, gmask);
         }
     }
-    // block reduction of the loss -> one float64 atomic per block
-    __shared__ double s_red[8];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
-    if (lane == 0) s_red[threadIdx.x >> 5] = loss;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double tot = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[w];
-        atomicAdd(a.loss, tot);
-    }
+    block_add_loss(loss, a.loss);
 }
 
 // torch.optim.Adam (single tensor, defaults: amsgrad off, weight_decay 0, maximize off), one launch for
@@ -175,17 +189,17 @@ __global__ void __launch_bounds__(256) hpf_map_predict_kernel(const void* users,
 
 
 // ------------------------------------------------------------------------------------------------
-// Lazy ("touch-only") Adam, exactly equivalent to torch's dense Adam.
+// Lazy ("touch-only") Adam, equivalent to torch's dense Adam.
 // torch.optim.Adam updates EVERY row at EVERY step: a row without gradient still decays m and v and moves
 // by -step_size*m/(sqrt(v)/bc2+eps).  Those zero-gradient steps depend only on the row's own (p, m, v) and on
-// per-step scalars, so they can be replayed in registers when the row is next touched: each row remembers the
-// last step it is up to date with (`last`); before a step's gradients are computed every row of the batch is
-// caught up to step t-1, after them only the touched rows take step t.  Traffic per step drops from
-// (N+M)(K+1)*28 bytes to the touched rows; arithmetic and results stay those of the dense kernel above.
+// per-step scalars, so they can be applied when the row is next referenced: each row remembers the last step it is up
+// to date with (`last`, see settle_row); when a step references a row, the row first takes its deferred real step and
+// the run of zero-gradient steps it skipped (closed form, RowCatchUp), then collects this step's gradient.  Traffic
+// per step drops from (N+M)(K+1)*28 bytes to the referenced rows.
 // ------------------------------------------------------------------------------------------------
 struct LazyState {   // mirrors pmf_lazy_adam in pmf_b200.h
     float *p[4], *m[4], *v[4], *g[4];          // theta (N,K), beta (M,K), xi (N), eta (M)
-    int32_t *last_user, *last_item, *claim_user, *claim_item, *touched_user, *touched_item, *counters;
+    int32_t *last_user, *last_item, *claim_user, *claim_item;
     const float *step_size, *bc2_sqrt;          // indexed by step number (1-based)
     float beta1, beta2, eps;
     const double *tail1, *tail2;                // closed-form catch-up tables (see RowCatchUp), or NULL: replay step by step
@@ -255,100 +269,115 @@ __device__ __forceinline__ void apply_catch_up(float& p, float& m, float& v, con
     v *= c.d2;
 }
 
-// catch one row (factor row `mat`: 0 theta / 1 beta, plus its scalar 2 xi / 3 eta) up to step t-1, zero its gradient
+// Row bookkeeping of the lazy scheme.  last[row] = s > 0: (p, m, v) are up to date with step s-1 and g[row] holds the
+// gradient of step s, NOT yet applied;  last[row] = -s <= 0: up to date with step s, nothing pending.
+// settle_row brings the row to "up to date with step t-1, gradient zeroed, pending at t": it applies the pending real
+// step (torch's update with the accumulated gradient), then the run of zero-gradient steps in closed form.
 template <int G>
-__device__ __forceinline__ void lazy_catch_up_row(const LazyState& L, int mat, int64_t row, int K, int t, int gl, int32_t* last) {
-    const RowCatchUp c = row_catch_up(L, last[row], t - 1);
+__device__ __forceinline__ void settle_row(const LazyState& L, int mat, int64_t row, int K, int t, int gl, unsigned gmask,
+                                           int32_t* last_arr) {
+    const int last = last_arr[row];
+    const int pending = last > 0 ? last : 0;
+    const RowCatchUp c = row_catch_up(L, last > 0 ? last : -last, t - 1);
     float* P = L.p[mat] + (size_t)row * K; float* Mo = L.m[mat] + (size_t)row * K; float* Vo = L.v[mat] + (size_t)row * K;
+    float* Gr = L.g[mat] + (size_t)row * K;
     for (int k = gl; k < K; k += G) {
-        if (c.J > 0) {
+        if (pending || c.J > 0) {
             float p = P[k], m = Mo[k], v = Vo[k];
+            if (pending) adam_one_step(p, m, v, Gr[k], pending, L);
             apply_catch_up(p, m, v, c, L);
             P[k] = p; Mo[k] = m; Vo[k] = v;
         }
-        L.g[mat][(size_t)row * K + k] = 0.f;
+        Gr[k] = 0.f;
     }
     if (gl == 0) {
-        if (c.J > 0) {
+        if (pending || c.J > 0) {
             float p = L.p[mat + 2][row], m = L.m[mat + 2][row], v = L.v[mat + 2][row];
+            if (pending) adam_one_step(p, m, v, L.g[mat + 2][row], pending, L);
             apply_catch_up(p, m, v, c, L);
             L.p[mat + 2][row] = p; L.m[mat + 2][row] = m; L.v[mat + 2][row] = v;
         }
         L.g[mat + 2][row] = 0.f;
     }
+    // publish: every lane's stores are visible device-wide before the row is marked ready for step t
+    __threadfence();
+    __syncwarp(gmask);
+    if (gl == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(last_arr + row), "r"(t) : "memory");
 }
 
+__device__ __forceinline__ void wait_row_ready(const int32_t* last_arr, int64_t row, int t) {
+    int v;
+    do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(last_arr + row) : "memory");
+    } while (v != t);
+}
+
+// ONE kernel per mini-batch step t (the reference does loss.backward() + a dense Adam step over every parameter,
+// compare_models.py:305-313).  A group of G lanes per batch element:
+//   1. claim: the first group of this step to see a row (atomicMax on claim[row]) settles it -- applies the row's pending
+//      Adam step, catches it up over the zero-gradient steps it skipped, zeroes its gradient -- and marks it ready;
+//   2. the other groups that reference the row spin until it is ready (the claimant is a RUNNING group, and it settles
+//      both of its rows before it waits for anything, so there is no cycle);
+//   3. loss terms + gradients of the element, float atomics into the rows' gradients.
+// The Adam step with the accumulated gradient is deferred to the row's next settle (or the final flush): kernel
+// boundaries order "all gradients of step t" before "the next settle of the row", so no grid-wide barrier is needed.
 template <int G, typename IdT>
-__global__ void __launch_bounds__(256) lazy_prepare_kernel(const LazyState L, const void* users, const void* items, int64_t B,
-                                                           int N, int M, int K, int t) {
+__global__ void __launch_bounds__(256) lazy_step_kernel(const LazyState L, const MapArgs a, int t) {
     const int lane = threadIdx.x & 31, gl = lane & (G - 1);
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    if (gid >= B) return;
-    const int64_t u = (int64_t)((const IdT*)users)[gid], it = (int64_t)((const IdT*)items)[gid];
-    if (u < 0 || u >= N || it < 0 || it >= M) return;   // reported by the gradient kernel
-    int first_u = 0, first_i = 0;
-    if (gl == 0) {
-        first_u = atomicMax(L.claim_user + u, t) < t;    // first group of this step to see the row owns its catch-up
-        first_i = atomicMax(L.claim_item + it, t) < t;
+    double loss = 0.0;
+    if (gid < a.B) {
+        const int64_t u = (int64_t)((const IdT*)a.users)[gid], it = (int64_t)((const IdT*)a.items)[gid];
+        if (u < 0 || u >= a.N || it < 0 || it >= a.M) {
+            if (gl == 0) atomicOr(a.bad, 1);   // torch indexing would raise IndexError
+        } else {
+            int first_u = 0, first_i = 0;
+            if (gl == 0) {
+                first_u = atomicMax(L.claim_user + u, t) < t;
+                first_i = atomicMax(L.claim_item + it, t) < t;
+            }
+            first_u = __shfl_sync(gmask, first_u, lane & ~(G - 1));
+            first_i = __shfl_sync(gmask, first_i, lane & ~(G - 1));
+            if (first_u) settle_row<G>(L, 0, u, a.K, t, gl, gmask, L.last_user);
+            if (first_i) settle_row<G>(L, 1, it, a.K, t, gl, gmask, L.last_item);
+            if (gl == 0) {
+                if (!first_u) wait_row_ready(L.last_user, u, t);
+                if (!first_i) wait_row_ready(L.last_item, it, t);
+            }
+            __syncwarp(gmask);
+            loss = map_element<G>(a, u, it, a.ratings[gid], gl, gmask);
+        }
     }
-    first_u = __shfl_sync(gmask, first_u, lane & ~(G - 1));
-    first_i = __shfl_sync(gmask, first_i, lane & ~(G - 1));
-    if (first_u) {
-        lazy_catch_up_row<G>(L, 0, u, K, t, gl, L.last_user);
-        if (gl == 0) L.touched_user[atomicAdd(L.counters + 0, 1)] = (int32_t)u;
-    }
-    if (first_i) {
-        lazy_catch_up_row<G>(L, 1, it, K, t, gl, L.last_item);
-        if (gl == 0) L.touched_item[atomicAdd(L.counters + 1, 1)] = (int32_t)it;
-    }
+    block_add_loss(loss, a.loss);
 }
 
-// the touched rows take step t with their accumulated gradient
-template <int G>
-__global__ void __launch_bounds__(256) lazy_update_kernel(const LazyState L, int K, int t) {
-    const int gl = threadIdx.x & (G - 1);
-    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const int nu = L.counters[0], ni = L.counters[1];
-    if (gid >= nu + ni) return;
-    const int mat = gid < nu ? 0 : 1;
-    const int64_t row = mat == 0 ? L.touched_user[gid] : L.touched_item[gid - nu];
-    for (int k = gl; k < K; k += G) {
-        const size_t e = (size_t)row * K + k;
-        float p = L.p[mat][e], m = L.m[mat][e], v = L.v[mat][e];
-        adam_one_step(p, m, v, L.g[mat][e], t, L);
-        L.p[mat][e] = p; L.m[mat][e] = m; L.v[mat][e] = v;
-    }
-    if (gl == 0) {
-        float p = L.p[mat + 2][row], m = L.m[mat + 2][row], v = L.v[mat + 2][row];
-        adam_one_step(p, m, v, L.g[mat + 2][row], t, L);
-        L.p[mat + 2][row] = p; L.m[mat + 2][row] = m; L.v[mat + 2][row] = v;
-        (mat == 0 ? L.last_user : L.last_item)[row] = t;
-    }
-}
-
-// bring every row up to step t (end of training / before the parameters are read from outside)
+// bring every row up to step t, nothing pending (end of training / before the parameters are read from outside)
 __global__ void __launch_bounds__(256) lazy_flush_kernel(const LazyState L, int N, int M, int K, int t) {
     const int lane = threadIdx.x & 31;
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wid >= (int64_t)N + M) return;
     const int mat = wid < N ? 0 : 1;
     const int64_t row = mat == 0 ? wid : wid - N;
-    int32_t* last = mat == 0 ? L.last_user : L.last_item;
-    const RowCatchUp c = row_catch_up(L, last[row], t);
-    if (c.J <= 0) return;
+    int32_t* last_arr = mat == 0 ? L.last_user : L.last_item;
+    const int last = last_arr[row];
+    const int pending = last > 0 ? last : 0;
+    const RowCatchUp c = row_catch_up(L, last > 0 ? last : -last, t);
+    if (!pending && c.J <= 0) return;
     for (int k = lane; k < K; k += 32) {
         const size_t e = (size_t)row * K + k;
         float p = L.p[mat][e], m = L.m[mat][e], v = L.v[mat][e];
+        if (pending) adam_one_step(p, m, v, L.g[mat][e], pending, L);
         apply_catch_up(p, m, v, c, L);
         L.p[mat][e] = p; L.m[mat][e] = m; L.v[mat][e] = v;
     }
     __syncwarp();
     if (lane == 0) {
         float p = L.p[mat + 2][row], m = L.m[mat + 2][row], v = L.v[mat + 2][row];
+        if (pending) adam_one_step(p, m, v, L.g[mat + 2][row], pending, L);
         apply_catch_up(p, m, v, c, L);
         L.p[mat + 2][row] = p; L.m[mat + 2][row] = m; L.v[mat + 2][row] = v;
-        last[row] = t;
+        last_arr[row] = -t;
     }
 }
 
@@ -434,10 +463,9 @@ static int lazy_state_from(const pmf_lazy_adam* st, LazyState& L) {
         PMF_REQUIRE(P[k] && Mo[k] && Vo[k] && Gr[k], "NULL parameter / moment / gradient tensor");
         L.p[k] = P[k]; L.m[k] = Mo[k]; L.v[k] = Vo[k]; L.g[k] = Gr[k];
     }
-    PMF_REQUIRE(st->last_user && st->last_item && st->claim_user && st->claim_item && st->touched_user &&
-                    st->touched_item && st->counters && st->step_size && st->bc2_sqrt, "NULL bookkeeping array");
+    PMF_REQUIRE(st->last_user && st->last_item && st->claim_user && st->claim_item && st->step_size && st->bc2_sqrt,
+                "NULL bookkeeping array");
     L.last_user = st->last_user; L.last_item = st->last_item; L.claim_user = st->claim_user; L.claim_item = st->claim_item;
-    L.touched_user = st->touched_user; L.touched_item = st->touched_item; L.counters = st->counters;
     L.step_size = st->step_size; L.bc2_sqrt = st->bc2_sqrt;
     L.beta1 = st->beta1; L.beta2 = st->beta2; L.eps = st->eps;
     PMF_REQUIRE((st->tail1 == nullptr) == (st->tail2 == nullptr), "tail1 and tail2 go together");
@@ -460,29 +488,29 @@ int pmf_hpf_map_lazy_epoch(const pmf_lazy_adam* st, const void* d_users, const v
     PMF_REQUIRE(d_users && d_items && d_ratings, "NULL batch");
     cudaStream_t s = (cudaStream_t)stream;
     const int G = K <= 64 ? 8 : 32;
+    MapArgs m;
+    m.theta = st->theta; m.beta = st->beta; m.xi = st->xi; m.eta = st->eta;
+    m.user_scale = d_user_scale; m.item_scale = d_item_scale; m.N = N; m.M = M; m.K = K;
+    m.a = a; m.a_prime = a_prime; m.b_prime = b_prime; m.c = c; m.c_prime = c_prime; m.d_prime = d_prime;
+    m.g_theta = st->g_theta; m.g_beta = st->g_beta; m.g_xi = st->g_xi; m.g_eta = st->g_eta;
+    m.loss = d_loss; m.bad = d_bad;
     int64_t t = step0;
     for (int64_t off = 0; off < n; off += batch) {
         const int64_t B = (n - off) < batch ? (n - off) : batch;
         ++t;
         PMF_REQUIRE(t < INT32_MAX, "too many steps");
-        const void* u = (const char*)d_users + off * id_bytes;
-        const void* it = (const char*)d_items + off * id_bytes;
-        PMF_CUDA(cudaMemsetAsync(L.counters, 0, 2 * sizeof(int32_t), s));
+        m.users = (const char*)d_users + off * id_bytes;
+        m.items = (const char*)d_items + off * id_bytes;
+        m.ratings = d_ratings + off;
+        m.B = B;
         const unsigned grid = (unsigned)cdiv(B * G, 256);
         if (G == 8) {
-            if (id_bytes == 8) lazy_prepare_kernel<8, int64_t><<<grid, 256, 0, s>>>(L, u, it, B, N, M, K, (int)t);
-            else lazy_prepare_kernel<8, int32_t><<<grid, 256, 0, s>>>(L, u, it, B, N, M, K, (int)t);
+            if (id_bytes == 8) lazy_step_kernel<8, int64_t><<<grid, 256, 0, s>>>(L, m, (int)t);
+            else lazy_step_kernel<8, int32_t><<<grid, 256, 0, s>>>(L, m, (int)t);
         } else {
-            if (id_bytes == 8) lazy_prepare_kernel<32, int64_t><<<grid, 256, 0, s>>>(L, u, it, B, N, M, K, (int)t);
-            else lazy_prepare_kernel<32, int32_t><<<grid, 256, 0, s>>>(L, u, it, B, N, M, K, (int)t);
+            if (id_bytes == 8) lazy_step_kernel<32, int64_t><<<grid, 256, 0, s>>>(L, m, (int)t);
+            else lazy_step_kernel<32, int32_t><<<grid, 256, 0, s>>>(L, m, (int)t);
         }
-        PMF_LAUNCH_CHECK();
-        PMF_TRY(pmf_hpf_map_loss_grad(u, it, id_bytes, d_ratings + off, B, st->theta, st->beta, st->xi, st->eta, d_user_scale,
-                                      d_item_scale, N, M, K, a, a_prime, b_prime, c, c_prime, d_prime, st->g_theta,
-                                      st->g_beta, st->g_xi, st->g_eta, d_loss, d_bad, stream));
-        const unsigned ugrid = (unsigned)cdiv(2 * B * G, 256);   // at most B touched rows per side
-        if (G == 8) lazy_update_kernel<8><<<ugrid, 256, 0, s>>>(L, K, (int)t);
-        else lazy_update_kernel<32><<<ugrid, 256, 0, s>>>(L, K, (int)t);
         PMF_LAUNCH_CHECK();
     }
     return PMF_OK;

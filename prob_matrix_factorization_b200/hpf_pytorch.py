@@ -25,7 +25,7 @@ import torch.nn.functional as F
 from . import _cabi
 
 
-LAZY_LAUNCHES_PER_STEP = 3     # pmf_hpf_map_lazy_epoch: catch-up, loss+gradient, touched-row Adam
+LAZY_LAUNCHES_PER_STEP = 1     # pmf_hpf_map_lazy_epoch: one fused settle + loss + gradient kernel per mini-batch
 
 @dataclass
 class HPF_PyTorch_Config:
@@ -154,10 +154,10 @@ class HPF_PyTorch(nn.Module):
         ``torch.randperm(n, generator=Generator().manual_seed(seed))`` -- replayed here bit for bit, so a
         run under the same ``torch.manual_seed`` visits the same mini-batches as the reference loop.
         ``lazy=False`` (default): one fused loss+gradient kernel and one dense Adam kernel per tensor per step.
-        ``lazy=True``: touch-only Adam -- rows without gradient are replayed in registers when next touched
-        (``pmf_hpf_map_lazy_epoch``; same arithmetic as the dense update, the whole epoch is enqueued by one C
-        call).  It moves ~250x fewer bytes but is currently SLOWER at C4 (133 vs 97 ms/epoch, profiles/README.md):
-        the replay is a dependent chain of IEEE sqrt + divides per skipped step.  Returns the list of epoch
+        ``lazy=True``: touch-only Adam (``pmf_hpf_map_lazy_epoch``): ONE kernel per mini-batch settles the rows the batch
+        references (their deferred Adam step + the zero-gradient steps they skipped, in closed form), then adds the
+        batch's loss and gradients; ~250x fewer bytes than the dense update and the same result up to float32 rounding
+        (tests: 1e-5 max-norm relative on parameters and moments).  Returns the list of epoch
         losses (sum of mini-batch losses, as the scripts print).  ``stats`` (a dict) receives ``device_ms`` -- CUDA-event
         time of the epochs, uploads excluded -- and ``launches`` (this library's kernels).
         """
@@ -247,43 +247,44 @@ class HPF_PyTorch(nn.Module):
         if "last_user" not in st:
             st.update(last_user=i32(self.n_users), last_item=i32(self.n_items), claim_user=i32(self.n_users),
                       claim_item=i32(self.n_items))
-            st["last_user"].fill_(st["step"]); st["last_item"].fill_(st["step"])
-        touched = (i32(batch_size), i32(batch_size), i32(2))
+            st["last_user"].fill_(-st["step"]); st["last_item"].fill_(-st["step"])    # up to date, nothing pending
         S = _cabi.LazyAdamState()
         for names, tensors in ((("theta", "beta", "xi", "eta"), params), (("m_theta", "m_beta", "m_xi", "m_eta"), st["m"]),
                                (("v_theta", "v_beta", "v_xi", "v_eta"), st["v"]), (("g_theta", "g_beta", "g_xi", "g_eta"), grads)):
             for nm, t in zip(names, tensors):
                 setattr(S, nm, t.data_ptr())
         for nm, t in (("last_user", st["last_user"]), ("last_item", st["last_item"]), ("claim_user", st["claim_user"]),
-                      ("claim_item", st["claim_item"]), ("touched_user", touched[0]), ("touched_item", touched[1]),
-                      ("counters", touched[2]), ("step_size", tab[0]), ("bc2_sqrt", tab[1])):
+                      ("claim_item", st["claim_item"]), ("step_size", tab[0]), ("bc2_sqrt", tab[1])):
             setattr(S, nm, t.data_ptr())
         S.beta1, S.beta2, S.eps = beta1, beta2, eps
         S.tail1, S.tail2 = (tails[0].data_ptr(), tails[1].data_ptr()) if closed_form else (None, None)
-        losses = []
         id_bytes = 8 if u_all.dtype == torch.int64 else 4
+        acc = torch.zeros(epochs, dtype=torch.float64, device=dev)      # one loss per epoch, read back once at the end
+        losses = []
         with torch.cuda.device(dev), torch.no_grad():
             for ep in range(epochs):
                 if shuffle:
+                    # (no host synchronisation inside the loop: the CPU draws epoch e+1's permutation while the GPU runs epoch e)
                     _base_seed = torch.empty((), dtype=torch.int64).random_()          # dataloader.py _BaseDataLoaderIter
                     seed = int(torch.empty((), dtype=torch.int64).random_().item())    # sampler.py RandomSampler.__iter__
                     gen = torch.Generator()
                     gen.manual_seed(seed)
-                    perm = torch.randperm(n, generator=gen).to(dev)
+                    perm = torch.randperm(n, generator=gen).pin_memory().to(dev, non_blocking=True)
                     u_ep, i_ep, r_ep = u_all[perm].contiguous(), i_all[perm].contiguous(), r_all[perm].contiguous()
                 else:
                     u_ep, i_ep, r_ep = u_all, i_all, r_all
-                acc = torch.zeros((), dtype=torch.float64, device=dev)
                 _cabi.call("pmf_hpf_map_lazy_epoch", C.byref(S), u_ep.data_ptr(), i_ep.data_ptr(), id_bytes, r_ep.data_ptr(), n,
                            batch_size, st["step"], self.user_scale.data_ptr(), self.item_scale.data_ptr(), self.n_users,
                            self.n_items, self.K, cfg.a, cfg.a_prime, cfg.b_prime, cfg.c, cfg.c_prime, cfg.d_prime,
-                           acc.data_ptr(), self._bad.data_ptr(), _cabi.stream_ptr())
+                           acc[ep:].data_ptr(), self._bad.data_ptr(), _cabi.stream_ptr())
                 st["step"] += steps_per_epoch
-                losses.append(float(acc.item()))
                 if on_epoch is not None:
                     self._lazy_flush(S, st)
+                    losses.append(float(acc[ep].item()))
                     on_epoch(ep, losses[-1])
             self._lazy_flush(S, st)
+            if on_epoch is None:
+                losses = [float(v) for v in acc.cpu().tolist()]
         self.check_ids()
         return losses
 
