@@ -73,6 +73,48 @@ class _FusedLoss(torch.autograd.Function):
         return g[0].mul_(gout), g[1].mul_(gout), g[2].mul_(gout), g[3].mul_(gout), None, None, None, None
 
 
+class _EpochPermutations:
+    """The DataLoader's shuffles, replayed bit for bit, off the critical path.
+
+    Per epoch the reference's loop draws ``_base_seed`` (dataloader.py ``_BaseDataLoaderIter.__init__``) and the sampler's
+    ``seed`` (sampler.py ``RandomSampler.__iter__``) from the global CPU generator and shuffles with
+    ``torch.randperm(n, generator=Generator().manual_seed(seed))``.  The two draws are cheap and sequential; the
+    permutation itself is a serial Fisher-Yates on the host (20-100 ms for 1.1 M ratings -- several times the GPU time
+    of the epoch it feeds), but permutations of different epochs only depend on their seeds, so they are computed by a
+    few host threads ahead of the GPU.  ``prefetch=False`` draws and shuffles epoch by epoch (needed when a callback
+    may itself use the global generator between epochs)."""
+
+    def __init__(self, n, epochs, device, prefetch=True, workers=8):
+        self.n, self.epochs, self.device = n, epochs, device
+        self.prefetch = prefetch and epochs > 1
+        self._futures = []
+        if self.prefetch:
+            from concurrent.futures import ThreadPoolExecutor
+            seeds = [self._draw_seed() for _ in range(epochs)]
+            self._pool = ThreadPoolExecutor(max_workers=min(workers, epochs))
+            self._futures = [self._pool.submit(self._permute, s) for s in seeds]
+
+    @staticmethod
+    def _draw_seed():
+        torch.empty((), dtype=torch.int64).random_()                         # _base_seed (value unused, draw kept)
+        return int(torch.empty((), dtype=torch.int64).random_().item())      # RandomSampler's seed
+
+    def _permute(self, seed):
+        gen = torch.Generator()
+        gen.manual_seed(seed)
+        perm = torch.randperm(self.n, generator=gen)
+        return perm.pin_memory() if torch.device(self.device).type == "cuda" else perm
+
+    def __iter__(self):
+        for ep in range(self.epochs):
+            perm = self._futures[ep].result() if self.prefetch else self._permute(self._draw_seed())
+            if self.prefetch:
+                self._futures[ep] = None
+            yield perm.to(self.device, non_blocking=True)
+        if self.prefetch:
+            self._pool.shutdown(wait=False)
+
+
 class HPF_PyTorch(nn.Module):
     def __init__(self, n_users, n_items, user_counts, item_counts, config: HPF_PyTorch_Config, device=None):
         super().__init__()
@@ -175,8 +217,9 @@ class HPF_PyTorch(nn.Module):
         grads = st.setdefault("g", [torch.zeros_like(p) for p in params])
         beta1, beta2, eps = 0.9, 0.999, 1e-8
         losses = []
+        # device time of the epochs, from the moment the first epoch's permutation is on its way to the GPU
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(torch.cuda.current_stream(dev))
+        self._ev0 = ev0
         steps_per_epoch = (n + batch_size - 1) // batch_size
         if lazy:
             losses = self._fit_epochs_lazy(u_all, i_all, r_all, epochs, batch_size, lr, shuffle, on_epoch, st, params,
@@ -187,15 +230,16 @@ class HPF_PyTorch(nn.Module):
                 stats.update(device_ms=ev0.elapsed_time(ev1), launches=epochs * (steps_per_epoch * LAZY_LAUNCHES_PER_STEP + 1))
             return losses
         with torch.cuda.device(dev), torch.no_grad():
+            perms = iter(_EpochPermutations(n, epochs, dev, prefetch=on_epoch is None)) if shuffle else None
             for ep in range(epochs):
                 if shuffle:
-                    _base_seed = torch.empty((), dtype=torch.int64).random_()          # dataloader.py _BaseDataLoaderIter
-                    seed = int(torch.empty((), dtype=torch.int64).random_().item())    # sampler.py RandomSampler.__iter__
-                    gen = torch.Generator()
-                    gen.manual_seed(seed)
-                    perm = torch.randperm(n, generator=gen).to(dev)
+                    perm = next(perms)
+                    if ep == 0:
+                        ev0.record(torch.cuda.current_stream(dev))
                     u_ep, i_ep, r_ep = u_all[perm], i_all[perm], r_all[perm]
                 else:
+                    if ep == 0:
+                        ev0.record(torch.cuda.current_stream(dev))
                     u_ep, i_ep, r_ep = u_all, i_all, r_all
                 acc = torch.zeros((), dtype=torch.float64, device=dev)
                 for s in range(0, n, batch_size):
@@ -262,16 +306,17 @@ class HPF_PyTorch(nn.Module):
         acc = torch.zeros(epochs, dtype=torch.float64, device=dev)      # one loss per epoch, read back once at the end
         losses = []
         with torch.cuda.device(dev), torch.no_grad():
+            # no host synchronisation inside the loop, and the permutations come from host threads running ahead
+            perms = iter(_EpochPermutations(n, epochs, dev, prefetch=on_epoch is None)) if shuffle else None
             for ep in range(epochs):
                 if shuffle:
-                    # (no host synchronisation inside the loop: the CPU draws epoch e+1's permutation while the GPU runs epoch e)
-                    _base_seed = torch.empty((), dtype=torch.int64).random_()          # dataloader.py _BaseDataLoaderIter
-                    seed = int(torch.empty((), dtype=torch.int64).random_().item())    # sampler.py RandomSampler.__iter__
-                    gen = torch.Generator()
-                    gen.manual_seed(seed)
-                    perm = torch.randperm(n, generator=gen).pin_memory().to(dev, non_blocking=True)
+                    perm = next(perms)
+                    if ep == 0:
+                        self._ev0.record(torch.cuda.current_stream(dev))
                     u_ep, i_ep, r_ep = u_all[perm].contiguous(), i_all[perm].contiguous(), r_all[perm].contiguous()
                 else:
+                    if ep == 0:
+                        self._ev0.record(torch.cuda.current_stream(dev))
                     u_ep, i_ep, r_ep = u_all, i_all, r_all
                 _cabi.call("pmf_hpf_map_lazy_epoch", C.byref(S), u_ep.data_ptr(), i_ep.data_ptr(), id_bytes, r_ep.data_ptr(), n,
                            batch_size, st["step"], self.user_scale.data_ptr(), self.item_scale.data_ptr(), self.n_users,

@@ -13,9 +13,14 @@ cfg = HPF_PyTorch_Config(n_factors=K, a=0.3, c=0.3, lr=5e-4)
 torch.manual_seed(0)
 m = HPF_PyTorch(N, M, np.bincount(u, minlength=N), np.bincount(i, minlength=M), cfg)
 lazy = os.environ.get("C4_DENSE") is None
-for ep in range(int(os.environ.get("C4_EPOCHS", 2))):
+for rep, E in enumerate((1, 1, int(os.environ.get("C4_EPOCHS", 8)))):
     st = {}
     t = time.perf_counter()
-    m.fit_epochs(u, i, x, epochs=1, batch_size=4096, lazy=lazy, stats=st)
+    m.fit_epochs(u, i, x, epochs=E, batch_size=4096, lazy=lazy, stats=st)
     torch.cuda.synchronize()
-    print(f"epoch {ep}: wall {1e3 * (time.perf_counter() - t):.1f} ms, device {st['device_ms']:.1f} ms", flush=True)
+    print(f"call {rep}: {E} epoch(s): wall {1e3 * (time.perf_counter() - t) / E:.1f} ms/epoch, device {st['device_ms'] / E:.2f} ms/epoch", flush=True)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+m.fit_epochs(u, i, x, epochs=4, batch_size=4096, lazy=lazy, shuffle=False)
+e1.record(); torch.cuda.synchronize()
+print(f"4 unshuffled epochs (no host permutation): {e0.elapsed_time(e1) / 4:.2f} ms/epoch on the device", flush=True)
