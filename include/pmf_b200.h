@@ -324,6 +324,10 @@ typedef struct pmf_lazy_adam {
      * A run of J zero-gradient steps after step s then moves p by (m/sqrt(v)) [W1 - eps/sqrt(v) W2], W = tail[s] -
      * ratio^J tail[s+J], and decays m, v by beta^J (first order in eps/sqrt(v); runs where that exceeds 1e-3 are replayed). */
     const double *tail1, *tail2;
+    /* with tail1 / tail2: float64 [5][n_pow] powers for run lengths J = 0 .. n_pow-1 (longer runs are replayed):
+     * beta1^J, beta2^J, (beta1/sqrt(beta2))^J, (beta1/beta2)^J, beta2^(-J/2) */
+    const double* pow5;
+    int32_t n_pow;
 } pmf_lazy_adam;
 /* One pass over n (already shuffled) ratings in mini-batches of `batch`, ONE kernel per step: the first lane group to
  * reference a row settles it (deferred Adam step + catch-up, gradient zeroed), the others wait for it, then every

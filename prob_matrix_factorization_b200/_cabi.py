@@ -30,7 +30,8 @@ class LazyAdamState(C.Structure):
     _fields_ = ([(n, VP) for n in ("theta", "beta", "xi", "eta", "m_theta", "m_beta", "m_xi", "m_eta", "v_theta", "v_beta",
                                    "v_xi", "v_eta", "g_theta", "g_beta", "g_xi", "g_eta", "last_user", "last_item",
                                    "claim_user", "claim_item", "step_size", "bc2_sqrt")]
-                + [("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("tail1", VP), ("tail2", VP)])
+                + [("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("tail1", VP), ("tail2", VP), ("pow5", VP),
+                   ("n_pow", C.c_int32)])
 
 
 PMF_EUNSUPPORTED = -4

@@ -15,6 +15,13 @@ namespace pmf {
 
 __device__ __forceinline__ float softplus_t(float z) { return z > 20.f ? z : log1pf(expf(z)); }        // F.softplus, threshold 20
 __device__ __forceinline__ float softplus_grad_t(float z) { return z > 20.f ? 1.f : 1.f / (1.f + expf(-z)); }
+// both at once, one exponential: softplus(z) = log1p(e^z), softplus'(z) = e^z / (1 + e^z)
+__device__ __forceinline__ void softplus_both(float z, float& sp, float& dsp) {
+    if (z > 20.f) { sp = z; dsp = 1.f; return; }
+    const float e = expf(z);
+    sp = log1pf(e);
+    dsp = __fdividef(e, 1.f + e);   // 2 ulp: the gradients are compared at 1e-5
+}
 
 struct MapArgs {
     const void *users, *items;   // int64 or int32
@@ -31,23 +38,23 @@ struct MapArgs {
 // Loss terms and gradients of ONE batch element (u, it, r), computed by the G lanes of a group (lane l owns factors
 // k = l, l+G, ...); gradients are added to the dense gradient tensors with float atomics (duplicate ids in a batch).
 // Returns the element's loss (valid in lane 0 of the group).
-template <int G>
+template <int G, int MAXV>   // K <= G * MAXV
 __device__ __forceinline__ double map_element(const MapArgs& a, int64_t u, int64_t it, float r, int gl, unsigned gmask) {
-    constexpr int MAXV = 8;   // K <= G * MAXV
     const float s = a.user_scale[u], t = a.item_scale[it];
     const float* tr = a.theta + (size_t)u * a.K;
     const float* br = a.beta + (size_t)it * a.K;
-    float th[MAXV], be[MAXV], traw[MAXV], braw[MAXV];
+    float th[MAXV], be[MAXV], dth_raw[MAXV], dbe_raw[MAXV];   // values and d softplus / d raw
     float dot = 0.f, sum_th = 0.f, sum_be = 0.f, sum_lth = 0.f, sum_lbe = 0.f;
 #pragma unroll
     for (int v = 0; v < MAXV; ++v) {
         const int k = gl + v * G;
         if (k < a.K) {
-            traw[v] = __ldcg(tr + k); braw[v] = __ldcg(br + k);   // L2: rows may have been settled by another SM in this kernel
-            th[v] = softplus_t(traw[v]); be[v] = softplus_t(braw[v]);
+            // L2 loads: the rows may have been settled by another SM earlier in this kernel
+            softplus_both(__ldcg(tr + k), th[v], dth_raw[v]);
+            softplus_both(__ldcg(br + k), be[v], dbe_raw[v]);
             dot = fmaf(th[v], be[v], dot);
             sum_th += th[v]; sum_be += be[v];
-            sum_lth += logf(th[v]); sum_lbe += logf(be[v]);
+            sum_lth += __logf(th[v]); sum_lbe += __logf(be[v]);   // loss only (reported per epoch, compared at 1e-5)
         }
     }
 #pragma unroll
@@ -58,18 +65,19 @@ __device__ __forceinline__ double map_element(const MapArgs& a, int64_t u, int64
         sum_lth += __shfl_xor_sync(gmask, sum_lth, o);
         sum_lbe += __shfl_xor_sync(gmask, sum_lbe, o);
     }
-    const float xr = __ldcg(a.xi + u), er = __ldcg(a.eta + it);
-    const float xi = softplus_t(xr), eta = softplus_t(er);
+    float xi, eta, dxi_raw, deta_raw;
+    softplus_both(__ldcg(a.xi + u), xi, dxi_raw);
+    softplus_both(__ldcg(a.eta + it), eta, deta_raw);
     const float lam = fmaxf(dot, 1e-6f);                         // hpf_pytorch.py:80
-    const float g = dot >= 1e-6f ? 1.f - r / lam : 0.f;          // clamp passes gradient only inside its range
+    const float g = dot >= 1e-6f ? 1.f - __fdividef(r, lam) : 0.f;   // clamp passes gradient only inside its range
 #pragma unroll
     for (int v = 0; v < MAXV; ++v) {
         const int k = gl + v * G;
         if (k < a.K) {
-            const float dth = g * be[v] + s * (xi - (a.a - 1.f) / th[v]);
-            const float dbe = g * th[v] + t * (eta - (a.c - 1.f) / be[v]);
-            atomicAdd(a.g_theta + (size_t)u * a.K + k, dth * softplus_grad_t(traw[v]));
-            atomicAdd(a.g_beta + (size_t)it * a.K + k, dbe * softplus_grad_t(braw[v]));
+            const float dth = g * be[v] + s * (xi - __fdividef(a.a - 1.f, th[v]));
+            const float dbe = g * th[v] + t * (eta - __fdividef(a.c - 1.f, be[v]));
+            atomicAdd(a.g_theta + (size_t)u * a.K + k, dth * dth_raw[v]);
+            atomicAdd(a.g_beta + (size_t)it * a.K + k, dbe * dbe_raw[v]);
         }
     }
     double loss = 0.0;
@@ -78,8 +86,8 @@ __device__ __forceinline__ double map_element(const MapArgs& a, int64_t u, int64
         const float lxi = logf(xi), leta = logf(eta);
         const float dxi = s * (-Kf * a.a / xi + sum_th - (a.a_prime - 1.f) / xi + a.b_prime);
         const float deta = t * (-Kf * a.c / eta + sum_be - (a.c_prime - 1.f) / eta + a.d_prime);
-        atomicAdd(a.g_xi + u, dxi * softplus_grad_t(xr));
-        atomicAdd(a.g_eta + it, deta * softplus_grad_t(er));
+        atomicAdd(a.g_xi + u, dxi * dxi_raw);
+        atomicAdd(a.g_eta + it, deta * deta_raw);
         // loss terms (hpf_pytorch.py:83, :145-152, :158-165, :169-173, :176-180)
         const float nll = lam - r * logf(lam);
         const float p_th = s * (-a.a * Kf * lxi + xi * sum_th - (a.a - 1.f) * sum_lth);
@@ -107,7 +115,7 @@ __device__ __forceinline__ void block_add_loss(double loss, double* out) {
 }
 
 // One group of G lanes per batch element.
-template <int G, typename IdT>
+template <int G, int V, typename IdT>
 __global__ void __launch_bounds__(256) hpf_map_loss_grad_kernel(const MapArgs a) {
     const int lane = threadIdx.x & 31, gl = lane & (G - 1);
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
@@ -118,7 +126,7 @@ __global__ void __launch_bounds__(256) hpf_map_loss_grad_kernel(const MapArgs a)
         if (u < 0 || u >= a.N || it < 0 || it >= a.M) {
             if (gl == 0) atomicOr(a.bad, 1);   // torch indexing would raise IndexError
         } else {
-            loss = map_element<G>(a, u, it, a.ratings[gid], gl, gmask);
+            loss = map_element<G, V>(a, u, it, a.ratings[gid], gl, gmask);
         }
     }
     block_add_loss(loss, a.loss);
@@ -203,6 +211,8 @@ struct LazyState {   // mirrors pmf_lazy_adam in pmf_b200.h
     const float *step_size, *bc2_sqrt;          // indexed by step number (1-based)
     float beta1, beta2, eps;
     const double *tail1, *tail2;                // closed-form catch-up tables (see RowCatchUp), or NULL: replay step by step
+    const double* pow5;                         // [5][n_pow]: beta1^J, beta2^J, rho^J, r2^J, beta2^(-J/2) for J = 0 .. n_pow-1
+    int32_t n_pow;
 };
 
 // Closed form of a run of zero-gradient steps.  After the row's last real step s0, step s = s0 + j does
@@ -222,29 +232,41 @@ struct RowCatchUp {
     float d1, d2;           // beta1^J, beta2^J
     float W1, W2;
     float dmax_num;         // eps * bc_to / sqrt(beta2^J): divided by sqrt(v_0) this is the largest d_s of the run
+    bool closed;            // tables available for this run (else: step-by-step replay)
 };
 
 __device__ __forceinline__ RowCatchUp row_catch_up(const LazyState& L, int last, int to) {
     RowCatchUp c;
     c.from = last + 1; c.to = to; c.J = to - last;
-    if (c.J <= 0 || L.tail1 == nullptr) { c.d1 = c.d2 = 1.f; c.W1 = c.W2 = 0.f; c.dmax_num = 0.f; return c; }
-    const double J = (double)c.J;
-    const double d1 = exp(J * log((double)L.beta1)), d2 = exp(J * log((double)L.beta2));
-    const double rhoJ = d1 / sqrt(d2), r2J = d1 / d2;
-    c.d1 = (float)d1; c.d2 = (float)d2;
-    c.W1 = (float)(L.tail1[last] - rhoJ * L.tail1[to]);
-    c.W2 = (float)(L.tail2[last] - r2J * L.tail2[to]);
-    c.dmax_num = (float)((double)L.eps * (double)L.bc2_sqrt[to] / sqrt(d2));
+    c.closed = L.tail1 != nullptr && c.J < L.n_pow;
+    if (c.J <= 0 || !c.closed) { c.d1 = c.d2 = 1.f; c.W1 = c.W2 = 0.f; c.dmax_num = 0.f; return c; }
+    // powers of the decay factors come from host-built float64 tables (a run is never longer than the call's step count):
+    // five loads instead of float64 exp / log / sqrt / divide sequences, which were ~1300 of the ~4600 warp instructions
+    // a batch element cost (ncu, profiles/README.md)
+    const double* T = L.pow5 + c.J;
+    const size_t n = (size_t)L.n_pow;
+    c.d1 = (float)T[0]; c.d2 = (float)T[n];
+    c.W1 = (float)(L.tail1[last] - T[2 * n] * L.tail1[to]);
+    c.W2 = (float)(L.tail2[last] - T[3 * n] * L.tail2[to]);
+    c.dmax_num = (float)((double)L.eps * (double)L.bc2_sqrt[to] * T[4 * n]);
     return c;
 }
 
-__device__ __forceinline__ void adam_zero_grad_steps(float& p, float& m, float& v, int from, int to, const LazyState& L) {
-    for (int s = from; s <= to; ++s) {          // same expressions as adam_dense_kernel with grad = 0
-        m = m + (0.f - m) * (1.f - L.beta1);
-        v = v * L.beta2 + (1.f - L.beta2) * 0.f * 0.f;
-        const float denom = sqrtf(v) / L.bc2_sqrt[s] + L.eps;
-        p = p - L.step_size[s] * (m / denom);
+// step-by-step replay of zero-gradient steps (same expressions as adam_dense_kernel with grad = 0): the fallback of the
+// closed form; by value and not inlined, so that it costs the hot path neither registers nor local memory
+__device__ __noinline__ float3 adam_zero_grad_replay(float p, float m, float v, int from, int to, const float* __restrict__ step_size,
+                                                     const float* __restrict__ bc2_sqrt, float beta1, float beta2, float eps) {
+    for (int s = from; s <= to; ++s) {
+        m = m + (0.f - m) * (1.f - beta1);
+        v = v * beta2 + (1.f - beta2) * 0.f * 0.f;
+        const float denom = sqrtf(v) / bc2_sqrt[s] + eps;
+        p = p - step_size[s] * (m / denom);
     }
+    return make_float3(p, m, v);
+}
+__device__ __forceinline__ void adam_zero_grad_steps(float& p, float& m, float& v, int from, int to, const LazyState& L) {
+    const float3 r = adam_zero_grad_replay(p, m, v, from, to, L.step_size, L.bc2_sqrt, L.beta1, L.beta2, L.eps);
+    p = r.x; m = r.y; v = r.z;
 }
 
 __device__ __forceinline__ void adam_one_step(float& p, float& m, float& v, float g, int s, const LazyState& L) {
@@ -256,14 +278,14 @@ __device__ __forceinline__ void adam_one_step(float& p, float& m, float& v, floa
 
 __device__ __forceinline__ void apply_catch_up(float& p, float& m, float& v, const RowCatchUp& c, const LazyState& L) {
     if (c.J <= 0) return;
-    if (L.tail1 == nullptr) { adam_zero_grad_steps(p, m, v, c.from, c.to, L); return; }
+    if (!c.closed) { adam_zero_grad_steps(p, m, v, c.from, c.to, L); return; }
     if (m != 0.f) {
-        const float sv = sqrtf(v);
-        if (!(c.dmax_num <= 1e-3f * sv)) {   // eps is not negligible against sqrt(v) somewhere in the run (or v == 0): replay
+        const float rs = rsqrtf(v);          // 1/sqrt(v) (2 ulp; the result is compared at 1e-5): no division, no IEEE sqrt
+        if (!(c.dmax_num * rs <= 1e-3f)) {   // eps is not negligible against sqrt(v) somewhere in the run (or v == 0): replay
             adam_zero_grad_steps(p, m, v, c.from, c.to, L);
             return;
         }
-        p = p - (m / sv) * (c.W1 - (L.eps / sv) * c.W2);
+        p = p - (m * rs) * (c.W1 - (L.eps * rs) * c.W2);
     }
     m *= c.d1;
     v *= c.d2;
@@ -273,36 +295,51 @@ __device__ __forceinline__ void apply_catch_up(float& p, float& m, float& v, con
 // gradient of step s, NOT yet applied;  last[row] = -s <= 0: up to date with step s, nothing pending.
 // settle_row brings the row to "up to date with step t-1, gradient zeroed, pending at t": it applies the pending real
 // step (torch's update with the accumulated gradient), then the run of zero-gradient steps in closed form.
-template <int G>
+template <int G, int V>   // K + 1 <= G * (V + 1)
 __device__ __forceinline__ void settle_row(const LazyState& L, int mat, int64_t row, int K, int t, int gl, unsigned gmask,
                                            int32_t* last_arr) {
     const int last = last_arr[row];
     const int pending = last > 0 ? last : 0;
     const RowCatchUp c = row_catch_up(L, last > 0 ? last : -last, t - 1);
-    float* P = L.p[mat] + (size_t)row * K; float* Mo = L.m[mat] + (size_t)row * K; float* Vo = L.v[mat] + (size_t)row * K;
-    float* Gr = L.g[mat] + (size_t)row * K;
-    for (int k = gl; k < K; k += G) {
-        if (pending || c.J > 0) {
-            float p = P[k], m = Mo[k], v = Vo[k];
-            if (pending) adam_one_step(p, m, v, Gr[k], pending, L);
-            apply_catch_up(p, m, v, c, L);
-            P[k] = p; Mo[k] = m; Vo[k] = v;
+    // elements 0..K-1 are the factor row, element K is the row's scalar (xi / eta): one pass, no single-lane tail.
+    // All loads of the row are issued before the first dependent instruction (one memory round trip per row, not one per
+    // element: the kernel is latency-bound -- ncu: 39 % warps active, 38 % of stalls on the long scoreboard).
+    constexpr int VS = V + 1;
+    float p[VS], m[VS], v[VS], g[VS];
+    const bool work = pending || c.J > 0;
+#pragma unroll
+    for (int q = 0; q < VS; ++q) {
+        const int k = gl + q * G;
+        if (work && k <= K) {
+            const bool vec = k < K;
+            const size_t e = vec ? (size_t)row * K + k : (size_t)row;
+            const int tb = vec ? mat : mat + 2;
+            p[q] = L.p[tb][e]; m[q] = L.m[tb][e]; v[q] = L.v[tb][e];
+            g[q] = pending ? L.g[tb][e] : 0.f;
         }
-        Gr[k] = 0.f;
     }
-    if (gl == 0) {
-        if (pending || c.J > 0) {
-            float p = L.p[mat + 2][row], m = L.m[mat + 2][row], v = L.v[mat + 2][row];
-            if (pending) adam_one_step(p, m, v, L.g[mat + 2][row], pending, L);
-            apply_catch_up(p, m, v, c, L);
-            L.p[mat + 2][row] = p; L.m[mat + 2][row] = m; L.v[mat + 2][row] = v;
+#pragma unroll
+    for (int q = 0; q < VS; ++q) {
+        const int k = gl + q * G;
+        if (k <= K) {
+            const bool vec = k < K;
+            const size_t e = vec ? (size_t)row * K + k : (size_t)row;
+            const int tb = vec ? mat : mat + 2;
+            if (work) {
+                if (pending) adam_one_step(p[q], m[q], v[q], g[q], pending, L);
+                apply_catch_up(p[q], m[q], v[q], c, L);
+                L.p[tb][e] = p[q]; L.m[tb][e] = m[q]; L.v[tb][e] = v[q];
+            }
+            L.g[tb][e] = 0.f;
         }
-        L.g[mat + 2][row] = 0.f;
     }
-    // publish: every lane's stores are visible device-wide before the row is marked ready for step t
-    __threadfence();
+    // publish: the group's stores happen-before lane 0's fence (warp barrier), the fence makes them visible device-wide
+    // before the row is marked ready for step t (release is cumulative)
     __syncwarp(gmask);
-    if (gl == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(last_arr + row), "r"(t) : "memory");
+    if (gl == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(last_arr + row), "r"(t) : "memory");
+    }
 }
 
 __device__ __forceinline__ void wait_row_ready(const int32_t* last_arr, int64_t row, int t) {
@@ -321,8 +358,8 @@ __device__ __forceinline__ void wait_row_ready(const int32_t* last_arr, int64_t 
 //   3. loss terms + gradients of the element, float atomics into the rows' gradients.
 // The Adam step with the accumulated gradient is deferred to the row's next settle (or the final flush): kernel
 // boundaries order "all gradients of step t" before "the next settle of the row", so no grid-wide barrier is needed.
-template <int G, typename IdT>
-__global__ void __launch_bounds__(256) lazy_step_kernel(const LazyState L, const MapArgs a, int t) {
+template <int G, int V, typename IdT>
+__global__ void __launch_bounds__(256, 4) lazy_step_kernel(const LazyState L, const MapArgs a, int t) {
     const int lane = threadIdx.x & 31, gl = lane & (G - 1);
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -339,14 +376,14 @@ __global__ void __launch_bounds__(256) lazy_step_kernel(const LazyState L, const
             }
             first_u = __shfl_sync(gmask, first_u, lane & ~(G - 1));
             first_i = __shfl_sync(gmask, first_i, lane & ~(G - 1));
-            if (first_u) settle_row<G>(L, 0, u, a.K, t, gl, gmask, L.last_user);
-            if (first_i) settle_row<G>(L, 1, it, a.K, t, gl, gmask, L.last_item);
+            if (first_u) settle_row<G, V>(L, 0, u, a.K, t, gl, gmask, L.last_user);
+            if (first_i) settle_row<G, V>(L, 1, it, a.K, t, gl, gmask, L.last_item);
             if (gl == 0) {
                 if (!first_u) wait_row_ready(L.last_user, u, t);
                 if (!first_i) wait_row_ready(L.last_item, it, t);
             }
             __syncwarp(gmask);
-            loss = map_element<G>(a, u, it, a.ratings[gid], gl, gmask);
+            loss = map_element<G, V>(a, u, it, a.ratings[gid], gl, gmask);
         }
     }
     block_add_loss(loss, a.loss);
@@ -385,6 +422,23 @@ __global__ void __launch_bounds__(256) lazy_flush_kernel(const LazyState L, int 
 
 using namespace pmf;
 
+// kernel<G, V, IdT>: V = factors per lane rounded up to 1, 2, 4 or 8 (the per-lane loops are unrolled V times)
+#define PMF_DISPATCH_V(kernel, G_, v_, args)                                                             \
+    do {                                                                                                 \
+        const int vv_ = (v_);                                                                            \
+        if (id_bytes == 8) {                                                                             \
+            if (vv_ <= 1) kernel<G_, 1, int64_t><<<grid, 256, 0, s>>> args;                              \
+            else if (vv_ <= 2) kernel<G_, 2, int64_t><<<grid, 256, 0, s>>> args;                         \
+            else if (vv_ <= 4) kernel<G_, 4, int64_t><<<grid, 256, 0, s>>> args;                         \
+            else kernel<G_, 8, int64_t><<<grid, 256, 0, s>>> args;                                       \
+        } else {                                                                                         \
+            if (vv_ <= 1) kernel<G_, 1, int32_t><<<grid, 256, 0, s>>> args;                              \
+            else if (vv_ <= 2) kernel<G_, 2, int32_t><<<grid, 256, 0, s>>> args;                         \
+            else if (vv_ <= 4) kernel<G_, 4, int32_t><<<grid, 256, 0, s>>> args;                         \
+            else kernel<G_, 8, int32_t><<<grid, 256, 0, s>>> args;                                       \
+        }                                                                                                \
+    } while (0)
+
 extern "C" {
 
 int pmf_hpf_map_loss_grad(const void* d_users, const void* d_items, int32_t id_bytes, const float* d_ratings,
@@ -409,12 +463,10 @@ int pmf_hpf_map_loss_grad(const void* d_users, const void* d_items, int32_t id_b
     cudaStream_t s = (cudaStream_t)stream;
     if (K <= 64) {
         const unsigned grid = (unsigned)cdiv(B * 8, 256);
-        if (id_bytes == 8) hpf_map_loss_grad_kernel<8, int64_t><<<grid, 256, 0, s>>>(m);
-        else hpf_map_loss_grad_kernel<8, int32_t><<<grid, 256, 0, s>>>(m);
+        PMF_DISPATCH_V(hpf_map_loss_grad_kernel, 8, (K + 7) / 8, (m));
     } else {
         const unsigned grid = (unsigned)cdiv(B * 32, 256);
-        if (id_bytes == 8) hpf_map_loss_grad_kernel<32, int64_t><<<grid, 256, 0, s>>>(m);
-        else hpf_map_loss_grad_kernel<32, int32_t><<<grid, 256, 0, s>>>(m);
+        PMF_DISPATCH_V(hpf_map_loss_grad_kernel, 32, (K + 31) / 32, (m));
     }
     PMF_LAUNCH_CHECK();
     return PMF_OK;
@@ -468,8 +520,10 @@ static int lazy_state_from(const pmf_lazy_adam* st, LazyState& L) {
     L.last_user = st->last_user; L.last_item = st->last_item; L.claim_user = st->claim_user; L.claim_item = st->claim_item;
     L.step_size = st->step_size; L.bc2_sqrt = st->bc2_sqrt;
     L.beta1 = st->beta1; L.beta2 = st->beta2; L.eps = st->eps;
-    PMF_REQUIRE((st->tail1 == nullptr) == (st->tail2 == nullptr), "tail1 and tail2 go together");
-    L.tail1 = st->tail1; L.tail2 = st->tail2;
+    PMF_REQUIRE((st->tail1 == nullptr) == (st->tail2 == nullptr) && (st->tail1 == nullptr) == (st->pow5 == nullptr),
+                "tail1, tail2 and pow5 go together");
+    PMF_REQUIRE(st->pow5 == nullptr || st->n_pow >= 1, "n_pow must be positive");
+    L.tail1 = st->tail1; L.tail2 = st->tail2; L.pow5 = st->pow5; L.n_pow = st->n_pow;
     return PMF_OK;
 }
 
@@ -504,13 +558,8 @@ int pmf_hpf_map_lazy_epoch(const pmf_lazy_adam* st, const void* d_users, const v
         m.ratings = d_ratings + off;
         m.B = B;
         const unsigned grid = (unsigned)cdiv(B * G, 256);
-        if (G == 8) {
-            if (id_bytes == 8) lazy_step_kernel<8, int64_t><<<grid, 256, 0, s>>>(L, m, (int)t);
-            else lazy_step_kernel<8, int32_t><<<grid, 256, 0, s>>>(L, m, (int)t);
-        } else {
-            if (id_bytes == 8) lazy_step_kernel<32, int64_t><<<grid, 256, 0, s>>>(L, m, (int)t);
-            else lazy_step_kernel<32, int32_t><<<grid, 256, 0, s>>>(L, m, (int)t);
-        }
+        if (G == 8) { PMF_DISPATCH_V(lazy_step_kernel, 8, (K + 7) / 8, (L, m, (int)t)); }
+        else { PMF_DISPATCH_V(lazy_step_kernel, 32, (K + 31) / 32, (L, m, (int)t)); }
         PMF_LAUNCH_CHECK();
     }
     return PMF_OK;

@@ -287,6 +287,9 @@ class HPF_PyTorch(nn.Module):
                 for s_ in range(total - 1, -1, -1):
                     tail[s_] = r * (c[s_ + 1] + tail[s_ + 1])
                 tails.append(torch.from_numpy(tail).to(dev))
+            Jr = np.arange(total + 2, dtype=np.float64)
+            pow5 = np.stack([beta1 ** Jr, beta2 ** Jr, (beta1 / math.sqrt(beta2)) ** Jr, (beta1 / beta2) ** Jr, beta2 ** (-0.5 * Jr)])
+            tails.append(torch.from_numpy(np.ascontiguousarray(pow5)).to(dev))
         i32 = lambda k: torch.zeros(k, dtype=torch.int32, device=dev)
         if "last_user" not in st:
             st.update(last_user=i32(self.n_users), last_item=i32(self.n_items), claim_user=i32(self.n_users),
@@ -301,7 +304,8 @@ class HPF_PyTorch(nn.Module):
                       ("claim_item", st["claim_item"]), ("step_size", tab[0]), ("bc2_sqrt", tab[1])):
             setattr(S, nm, t.data_ptr())
         S.beta1, S.beta2, S.eps = beta1, beta2, eps
-        S.tail1, S.tail2 = (tails[0].data_ptr(), tails[1].data_ptr()) if closed_form else (None, None)
+        S.tail1, S.tail2, S.pow5 = (tails[0].data_ptr(), tails[1].data_ptr(), tails[2].data_ptr()) if closed_form else (None, None, None)
+        S.n_pow = total + 2
         id_bytes = 8 if u_all.dtype == torch.int64 else 4
         acc = torch.zeros(epochs, dtype=torch.float64, device=dev)      # one loss per epoch, read back once at the end
         losses = []
