@@ -13,6 +13,7 @@ The reference's tuning / compare / train scripts import the models by module pat
 run unchanged on top of libpmf_b200:
 
     python -m prob_matrix_factorization_b200.dropin --reference /path/to/reference src.experiments.train_all_models --dataset_mode full
+    python -m prob_matrix_factorization_b200.dropin --stub-matplotlib --script my_driver.py [args]     (a file instead of a module)
 
 If the reference checkout is on ``sys.path`` its other packages (``src.experiments``, ``src.data`` ...)
 are used as they are; without it, stub ``src`` / ``src.models`` / ``src.evaluation`` packages are created so
@@ -75,6 +76,8 @@ def stub_matplotlib():
 
     class _Anything(types.ModuleType):
         def __getattr__(self, name):
+            if name.startswith("__") and name.endswith("__"):      # inspect / importlib probe modules for __file__, __spec__ ...
+                raise AttributeError(name)
             return _Anything(name)
 
         def __call__(self, *a, **k):
@@ -93,19 +96,26 @@ def stub_matplotlib():
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     ref = os.environ.get("PMF_REFERENCE_ROOT")
+    script = None
     while argv and argv[0].startswith("--"):
         flag = argv.pop(0)
         if flag == "--reference":
             ref = argv.pop(0)
         elif flag == "--stub-matplotlib":
             stub_matplotlib()
+        elif flag == "--script":
+            script = argv[0]
+            break
         else:
             raise SystemExit(f"unknown flag {flag}")
     if not argv:
         raise SystemExit(__doc__)
     install(ref)
-    module, sys.argv = argv[0], argv
-    runpy.run_module(module, run_name="__main__", alter_sys=True)
+    sys.argv = argv
+    if script is not None:
+        runpy.run_path(script, run_name="__main__")
+    else:
+        runpy.run_module(argv[0], run_name="__main__", alter_sys=True)
 
 
 if __name__ == "__main__":

@@ -14,7 +14,8 @@ import numpy as np
 import torch
 
 from . import _cabi
-from ._engine import EvalSet, eval_stats, normalise_ids, pad_table, predict, row_stride, table_to_host
+from ._engine import (DeviceLoop, EvalSet, device_loop_enabled, eval_stats, eval_stats_launch, normalise_ids, pad_table,
+                      predict, row_stride, table_to_host)
 from .poisson_mf_cavi import _DeviceBacked
 from .ratings import DEFAULT_SEG_LEN, DeviceRatings, to_device
 
@@ -181,7 +182,10 @@ class GaussianMFCAVI(_DeviceBacked):
             ev = EvalSet(val[0], val[1], val[2], self.n_users, self.n_items, eng.dev, drop_invalid=True)
         eta_bias2 = getattr(cfg, "eta_bias2", 1.0)
         prev_val_rmse = None
-        for it in range(1, cfg.max_iter + 1):
+        host_iters = range(1, cfg.max_iter + 1)
+        if device_loop_enabled() and not cfg.verbose and cfg.max_iter >= 1:
+            host_iters = self._fit_on_device(eng, ev, eta_bias2)
+        for it in host_iters:
             if cfg.verbose:
                 print(f"\nCAVI iteration {it}/{cfg.max_iter}")
             eng.sweep(cfg.sigma2, cfg.eta_theta2, cfg.eta_beta2, eta_bias2)
@@ -208,6 +212,30 @@ class GaussianMFCAVI(_DeviceBacked):
                 prev_val_rmse = val_rmse
         self._invalidate()
         return self
+
+    def _fit_on_device(self, eng, ev, eta_bias2):
+        """The whole loop (4 passes + validation statistics + the stopping rule 0 <= improvement < tol, :279) as one
+        CUDA graph with a device-side WHILE (DeviceLoop).  Returns the iterations left for the host loop."""
+        cfg = self.config
+        try:
+            loop = DeviceLoop(eng.dev, cfg.max_iter, ev_out=None if ev is None else ev.out, rule=1,
+                              tol=None if ev is None else cfg.tol)
+            with loop.body():
+                eng.sweep(cfg.sigma2, cfg.eta_theta2, cfg.eta_beta2, eta_bias2)
+                if ev is not None:
+                    eval_stats_launch(ev, eng.m_theta, eng.m_beta, self.n_users, self.n_items, eng.K, eng.ld, eng.b_user,
+                                      eng.b_item, self.global_mean)
+        except _cabi.PMFError as exc:
+            if exc.status != _cabi.PMF_EUNSUPPORTED:
+                raise
+            return range(1, cfg.max_iter + 1)
+        self.n_iter_, hist = loop.run()
+        loop.free()
+        self.val_rmse_history_ = [float(v) for v in hist]
+        for v in self.val_rmse_history_:
+            if np.isnan(v):
+                print("Warning: No valid (u,i) pairs.")
+        return range(0)
 
     def _eval(self, ev):
         e = self._engine

@@ -83,3 +83,29 @@ def test_configs_and_methods_match_reference(mod, cfg, cls):
     our_cls = getattr(ours, cls)
     missing = {n for n in ref_methods if not hasattr(our_cls, n)}
     assert not missing, missing
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/experiments"), reason="reference checkout not present")
+def test_reference_scripts_import_the_engine_through_dropin():
+    """The reference's own driver modules (train_*_full.py, compare_models.py, tune_all_models.py), imported UNMODIFIED
+    from the read-only checkout with ``dropin.install`` + ``stub_matplotlib``, bind our classes (no fit here: no GPU)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.dont_write_bytecode = True\n"
+        "from prob_matrix_factorization_b200 import dropin\n"
+        "dropin.stub_matplotlib(); dropin.install('/root/reference')\n"
+        "import src.experiments.train_poisson_full as tp, src.experiments.train_hpf_cavi_full as th\n"
+        "import src.experiments.train_gaussian_full as tg, src.experiments.compare_models as cm\n"
+        "import prob_matrix_factorization_b200.poisson_mf_cavi as ours_p, prob_matrix_factorization_b200.hpf_cavi as ours_h\n"
+        "import prob_matrix_factorization_b200.gaussian_mf_cavi_bias as ours_g, prob_matrix_factorization_b200.hpf_pytorch as ours_t\n"
+        "assert tp.PoissonMFCAVI is ours_p.PoissonMFCAVI and tp.PoissonMFCAVIConfig is ours_p.PoissonMFCAVIConfig\n"
+        "assert th.HPF_CAVI is ours_h.HPF_CAVI and tg.GaussianMFCAVI is ours_g.GaussianMFCAVI\n"
+        "assert cm.HPF_PyTorch is ours_t.HPF_PyTorch and cm.PoissonMFCAVI is ours_p.PoissonMFCAVI\n"
+        "hp = cm.load_best_hyperparams('/root/reference/best_hyperparams.txt')\n"
+        "cfg = ours_p.PoissonMFCAVIConfig(**hp['PoissonMF']); assert cfg.n_factors > 0\n"
+        "print('DROPIN_IMPORTS_OK')\n")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1", PYTHONPATH=repo)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp", timeout=300)
+    assert "DROPIN_IMPORTS_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
