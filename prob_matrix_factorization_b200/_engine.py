@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .parallel import RowExchange, owned_item_ranges
+from .parallel import RowExchange, item_chunk_bounds, owned_item_ranges
 from .ratings import DeviceRatings, Grouped, as_id_array, to_device
 
 MAX_DEVICE_LABELS = 64
@@ -134,13 +134,16 @@ def eval_stats_launch(ev, F_user, F_item, n_users, n_items, K, ld, b_user=None, 
 _SIDE_STREAMS = {}
 
 
-def side_stream(dev, which="loop"):
+def side_stream(dev, which="loop", high_priority=False):
     """One long-lived non-default stream per (device, purpose): creating a stream costs 25-900 ms on a cold context
-    (measured inside fits, profiles/README.md), far more than a small fit."""
+    (measured inside fits, profiles/README.md), far more than a small fit.  ``high_priority``: the block scheduler
+    hands freed SM slots to this stream's kernels first -- what lets the cross-rank combine of one item chunk run
+    WHILE the pass over the next chunk (whose grid fills the GPU many times over) is still executing."""
     dev = torch.device(dev)
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), which)
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+        prio = torch.cuda.Stream.priority_range()[1] if high_priority else 0
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev, priority=prio)
     return _SIDE_STREAMS[key]
 
 
@@ -315,7 +318,7 @@ class GammaEngine:
         n_item_tiles = len(ratings.item_tiles)
         if self.exchange == "mc":
             self.E_beta, self.acc_item = self._symm["E_beta"][0], self._symm["acc_item"][0]
-            self._side = side_stream(self.dev, "combine")
+            self._side = side_stream(self.dev, "combine", high_priority=True)
         else:
             self.E_beta = f(self.M)
             self.acc_item = f(self.M, 2 * self.ld) if (self.world > 1 or n_item_tiles > 1) else None
@@ -335,9 +338,8 @@ class GammaEngine:
             item_chunks = ratings.item_chunks
         self.item_chunks = max(1, min(int(item_chunks), self.M)) if self.exchange == "mc" else 1
         if self.item_chunks > 1:
-            C_ = self.item_chunks
-            cb = [self.M * c // C_ for c in range(C_ + 1)]
-            self.item_lists = [[g.slice(cb[c], cb[c + 1]) for g in ratings.item_tiles] for c in range(C_)]
+            cb = item_chunk_bounds(self.M, self.item_chunks)
+            self.item_lists = [[g.slice(cb[c], cb[c + 1]) for g in ratings.item_tiles] for c in range(self.item_chunks)]
         else:
             self.item_lists = [list(ratings.item_tiles)]
         self.owned_items = owned_item_ranges(self.M, self.item_chunks, self.world, self.rank) if self.world > 1 else []

@@ -65,15 +65,29 @@ def balanced_bounds_from_counts(counts, parts):
     return balanced_row_bounds(row_ptr, parts)
 
 
-def owned_item_ranges(n_items, chunks, world, rank):
-    """Item rows whose combine step `rank` performs: the rank's share of each of `chunks` equal item ranges.
+def item_chunk_bounds(n_items, chunks):
+    """Item-row chunks of the multi-GPU item pass, in processing order: sizes proportional to chunks, chunks-1, ..., 1.
 
-    Chunk c = [n_items*c//chunks, n_items*(c+1)//chunks); inside it rank r owns the r-th of `world` equal parts.
-    (Chunks exist so that the cross-rank combine of one chunk overlaps the item pass of the next.)"""
-    out = []
+    The cross-rank combine of a chunk overlaps the pass over the next one; only the LAST chunk's combine is exposed, so
+    the last chunk is the smallest (40/30/20/10 % for 4 chunks)."""
+    chunks = max(1, min(int(chunks), int(n_items)))
+    total = chunks * (chunks + 1) // 2
+    bounds, acc = [0], 0
     for c in range(chunks):
-        lo, hi = n_items * c // chunks, n_items * (c + 1) // chunks
-        n = hi - lo
+        acc += chunks - c
+        bounds.append(max(bounds[-1] + 1, n_items * acc // total) if c < chunks - 1 else n_items)
+    for c in range(chunks - 1, 0, -1):          # tiny inputs: keep every chunk non-empty
+        bounds[c] = min(bounds[c], bounds[c + 1] - 1)
+    return bounds
+
+
+def owned_item_ranges(n_items, chunks, world, rank):
+    """Item rows whose combine step `rank` performs: the rank's share of each chunk of item_chunk_bounds()
+    (inside a chunk rank r owns the r-th of `world` equal parts)."""
+    b = item_chunk_bounds(n_items, chunks)
+    out = []
+    for c in range(len(b) - 1):
+        lo, n = b[c], b[c + 1] - b[c]
         out.append((lo + n * rank // world, lo + n * (rank + 1) // world))
     return out
 

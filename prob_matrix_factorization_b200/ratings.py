@@ -233,13 +233,17 @@ class DeviceRatings:
         self.seg_len_user = seg_len if seg_len is not None else auto_seg_len(self.nnz_local // launches_u)
         self.seg_len_item = seg_len if seg_len is not None else auto_seg_len(self.nnz_local // launches_i)
         self.seg_len = self.seg_len_user
+        from ._engine import Trace
+        tr = Trace()
         with torch.cuda.device(device):
             u_loc = u_d - self.user_lo if self.user_lo else u_d     # rows of the user pass are local to the rank's range
             self.user_tiles = self._build_tiles(u_loc, i_d, x_d, self.item_tile_bounds, by_item=True, key_is_user=True,
                                                 n_rows=n_own, row_offset=self.user_lo, seg_len=self.seg_len_user) if n_own > 0 else []
             del u_loc                                               # columns of the item pass are global user ids
+            tr.mark("  build: user-pass lists")
             self.item_tiles = self._build_tiles(u_d, i_d, x_d, self.user_tile_bounds, by_item=False, key_is_user=False,
                                                 n_rows=self.n_items, row_offset=0, seg_len=self.seg_len_item)
+            tr.mark("  build: item-pass lists")
         del u_d, i_d, x_d
 
     # -- construction helpers -------------------------------------------------------------------
@@ -261,6 +265,8 @@ class DeviceRatings:
         """Upload this rank's piece of the list and exchange ratings so that each rank holds its user range's."""
         import torch.distributed as dist
         from .parallel import balanced_bounds_from_counts
+        from ._engine import Trace
+        tr = Trace()
         dev, W, r = self.device, self.world, self.rank
         if shard_input == "full":
             n = len(u_h)
@@ -273,6 +279,7 @@ class DeviceRatings:
         i_c = to_device(i_h, dev, torch.int32)
         x_c = to_device(x_h, dev, torch.float32)
         self.h2d_bytes = u_c.numel() * 12
+        tr.mark("  route: upload of this rank's piece")
         counts = torch.empty(self.n_users, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             _cabi.call("pmf_count_keys", u_c.data_ptr(), u_c.numel(), self.n_users, counts.data_ptr(), _cabi.stream_ptr())
@@ -281,6 +288,7 @@ class DeviceRatings:
         tot = torch.tensor([u_c.numel()], dtype=torch.int64, device=dev)
         dist.all_reduce(tot)
         self.nnz = int(tot.item())
+        tr.mark("  route: ratings per user (count + all-reduce) and owner ranges")
         # stable split of the piece by owner, then one all-to-all: pieces arrive in rank order = list order, so every
         # rank ends with its users' ratings in ORIGINAL order (what the reference's per-row lists contain)
         u_s, i_s, x_s, offs = coo_partition(u_c, i_c, x_c, self.user_bounds, by_item=False)
@@ -288,12 +296,14 @@ class DeviceRatings:
         recv = torch.empty(W, dtype=torch.int64, device=dev)
         dist.all_to_all_single(recv, send)
         send_l, recv_l = [int(v) for v in np.diff(offs)], [int(v) for v in recv.cpu().tolist()]
+        tr.mark("  route: stable split by owner + counts exchange")
         n_loc = sum(recv_l)
         out = []
         for src in (u_s, i_s, x_s):
             dst = torch.empty(n_loc, dtype=src.dtype, device=dev)
             dist.all_to_all_single(dst, src, recv_l, send_l)
             out.append(dst)
+        tr.mark("  route: all-to-all of (u, i, rating)")
         return out
 
     # -- views ---------------------------------------------------------------------------------------

@@ -88,3 +88,35 @@ def test_sharded_sweeps_equal_single_rank_gloo():
     for rank, err, nbytes in res:
         assert err < 1e-12, (rank, err)      # row-aligned shards: bit-identical maths, no cross-rank sums
         assert nbytes > 0
+
+
+def test_item_chunks_and_owned_ranges_partition_the_items():
+    """Multi-GPU item pass: chunks (processing order, shrinking sizes) x ranks tile [0, n_items) exactly once."""
+    from prob_matrix_factorization_b200.parallel import item_chunk_bounds, owned_item_ranges
+    for n_items, chunks, world in [(500_000, 4, 8), (10, 4, 3), (3, 4, 2), (7, 1, 8), (12_000, 3, 4), (5, 8, 8)]:
+        b = item_chunk_bounds(n_items, chunks)
+        assert b[0] == 0 and b[-1] == n_items and all(x < y for x, y in zip(b, b[1:]))
+        sizes = [y - x for x, y in zip(b, b[1:])]
+        assert sizes == sorted(sizes, reverse=True) or n_items < 20          # the exposed (last) chunk is the smallest
+        seen = np.zeros(n_items, dtype=np.int32)
+        for r in range(world):
+            ranges = owned_item_ranges(n_items, chunks, world, r)
+            assert len(ranges) == len(b) - 1
+            for c, (lo, hi) in enumerate(ranges):
+                assert b[c] <= lo <= hi <= b[c + 1]
+                seen[lo:hi] += 1
+        assert (seen == 1).all()
+
+
+def test_balanced_bounds_from_counts():
+    from prob_matrix_factorization_b200.parallel import balanced_bounds_from_counts, balanced_row_bounds
+    rng = np.random.default_rng(0)
+    counts = rng.integers(0, 50, size=1000)
+    counts[17] = 5000                                              # one heavy row
+    for parts in (1, 2, 3, 8):
+        b = balanced_bounds_from_counts(counts, parts)
+        row_ptr = np.concatenate([[0], np.cumsum(counts)])
+        assert np.array_equal(b, balanced_row_bounds(row_ptr, parts))
+        assert b[0] == 0 and b[-1] == 1000 and np.all(np.diff(b) >= 0)
+        per = np.array([counts[b[p]:b[p + 1]].sum() for p in range(parts)])
+        assert per.sum() == counts.sum() and per.max() <= counts.sum() / parts + counts.max()
