@@ -297,6 +297,7 @@ class GammaEngine:
         self.exchange = exchange if self.world > 1 else "none"
         self._symm = {}
         self._side = None
+        self._ready = None        # events of an item pass whose combines are still in flight (see item_pass(join=False))
         if self.exchange == "mc":
             import torch.distributed as dist
             ok, why = 1.0, ""
@@ -453,19 +454,38 @@ class GammaEngine:
         h = self.hyper
         tiles = self.r.user_tiles
         wp = write_params and self.keep_params
+        main = torch.cuda.current_stream(self.dev)
+        # combines of the previous item pass that are still in flight: tile t gathers E_beta rows of item chunk t only
+        per_tile = self._ready if (self._ready and len(self._ready) == len(tiles)) else None
+        if self._ready and per_tile is None:
+            self._join()
         for t, g in enumerate(tiles):
+            if per_tile is not None:
+                main.wait_event(per_tile[t])
             last = t == len(tiles) - 1
             flags = (PMF_ACC_IN if t > 0 else 0) | (0 if last else PMF_ACC_OUT)
             self._pass(g, self.E_beta, self.E_theta, self.shp_theta if wp else None, self.rte_theta if wp else None,
                        self.user_shape, self.user_rate, self.E_xi, self.rate_xi, self.E_xi,
                        h["user_shape"] if h else 0.0, h["user_rate_prior"] if h else 0.0, self.ws_user,
                        self.acc_user, self.user_lo, flags)
+        if per_tile is not None:
+            self._join()
 
-    def item_pass(self, write_params=True):
+    def _join(self):
+        """The current stream waits for the cross-rank combines still running on the side stream."""
+        if self._ready:
+            torch.cuda.current_stream(self.dev).wait_stream(self._side)
+            self._ready = None
+
+    def item_pass(self, write_params=True, join=True):
+        """``join=False`` (multicast combine): return with the combines still in flight on the side stream; the next
+        ``user_pass`` waits for them tile by tile (every other consumer of E_beta must call ``_join`` first)."""
         h = self.hyper
         wp = write_params and self.keep_params
         self._item_params_synced = self.exchange != "mc"
         main = torch.cuda.current_stream(self.dev)
+        self._join()
+        ready = []
         for c, tiles in enumerate(self.item_lists):
             for t, g in enumerate(tiles):
                 last = t == len(tiles) - 1 and self.world == 1
@@ -479,13 +499,21 @@ class GammaEngine:
                 done.record(main)
                 self._side.wait_event(done)
                 with torch.cuda.stream(self._side):
-                    self._rank_barrier()                        # every rank has parked its sums of chunk c
+                    # one barrier says: every rank has parked its sums of chunk c AND finished its combine of chunk c-1
+                    self._rank_barrier()
+                    if c > 0:
+                        ready.append(torch.cuda.Event())
+                        ready[-1].record(self._side)            # E_beta rows of chunk c-1 are final on every replica
                     lo, hi = self.owned_items[c]
                     self._combine(lo, hi, write_params, multicast=True)
         if self.exchange == "mc":
             with torch.cuda.stream(self._side):
                 self._rank_barrier()                            # every rank's new E_beta rows have landed everywhere
-            main.wait_stream(self._side)
+                ready.append(torch.cuda.Event())
+                ready[-1].record(self._side)
+            self._ready = ready
+            if join:
+                self._join()
         elif self.exchange == "nccl":
             import torch.distributed as dist
             dist.all_reduce(self.acc_item)
@@ -497,6 +525,15 @@ class GammaEngine:
         with torch.cuda.device(self.dev):
             self.user_pass(write_params)
             self.item_pass(write_params)
+
+    def sweeps(self, n, write_params_last=True):
+        """``n`` iterations back to back.  On several GPUs the sweeps are software-pipelined: the combines of an item pass
+        run on the side stream while the next sweep's user pass works through the item chunks that are already final."""
+        with torch.cuda.device(self.dev):
+            for s in range(n):
+                wp = write_params_last and s == n - 1
+                self.user_pass(wp)
+                self.item_pass(wp, join=s == n - 1)
 
     def close(self):
         """Detach from the symmetric-memory tables (multi-GPU): state becomes ordinary device tensors and the tables go

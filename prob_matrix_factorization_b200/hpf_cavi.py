@@ -163,6 +163,10 @@ class HPF_CAVI(_DeviceBacked):
         if (device_loop_enabled() and not cfg.verbose and eng.world == 1 and self._allocation == "mean"
                 and not self._track_elbo and cfg.max_iter >= 1):
             host_iters = self._fit_on_device(eng, ev, params_every_sweep)
+        if eng.world > 1 and ev is None and not cfg.verbose and cfg.max_iter >= 1 and self._allocation == "mean" and not self._track_elbo:
+            eng.sweeps(cfg.max_iter)          # software-pipelined across sweeps (combine of sweep s under user pass s+1)
+            self.n_iter_ = cfg.max_iter
+            host_iters = range(0)
         for it in host_iters:
             if cfg.verbose:
                 print(f"\nHPF_CAVI iteration {it}/{cfg.max_iter}")

@@ -66,19 +66,12 @@ def balanced_bounds_from_counts(counts, parts):
 
 
 def item_chunk_bounds(n_items, chunks):
-    """Item-row chunks of the multi-GPU item pass, in processing order: sizes proportional to chunks, chunks-1, ..., 1.
+    """Item-row chunks of the multi-GPU sweep, in processing order: `chunks` equal ranges (int list, chunks+1 entries).
 
-    The cross-rank combine of a chunk overlaps the pass over the next one; only the LAST chunk's combine is exposed, so
-    the last chunk is the smallest (40/30/20/10 % for 4 chunks)."""
+    The item pass parks its row sums chunk by chunk; the cross-rank combine of chunk c (side stream) overlaps the pass over
+    the later chunks and -- the user pass being tiled over the SAME item ranges -- the next sweep's user-pass tiles < c."""
     chunks = max(1, min(int(chunks), int(n_items)))
-    total = chunks * (chunks + 1) // 2
-    bounds, acc = [0], 0
-    for c in range(chunks):
-        acc += chunks - c
-        bounds.append(max(bounds[-1] + 1, n_items * acc // total) if c < chunks - 1 else n_items)
-    for c in range(chunks - 1, 0, -1):          # tiny inputs: keep every chunk non-empty
-        bounds[c] = min(bounds[c], bounds[c + 1] - 1)
-    return bounds
+    return [n_items * c // chunks for c in range(chunks + 1)]
 
 
 def owned_item_ranges(n_items, chunks, world, rank):

@@ -174,6 +174,10 @@ class PoissonMFCAVI(_DeviceBacked):
         host_iters = range(1, cfg.max_iter + 1)
         if device_loop_enabled() and not cfg.verbose and eng.world == 1 and cfg.max_iter >= 1:
             host_iters = self._fit_on_device(eng, ev, params_every_sweep)
+        if eng.world > 1 and ev is None and not cfg.verbose and cfg.max_iter >= 1:
+            eng.sweeps(cfg.max_iter)          # software-pipelined across sweeps (combine of sweep s under user pass s+1)
+            self.n_iter_ = cfg.max_iter
+            host_iters = range(0)
         for it in host_iters:
             if cfg.verbose:
                 print(f"\nCAVI iteration {it}/{cfg.max_iter}")

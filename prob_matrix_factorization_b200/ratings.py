@@ -224,8 +224,14 @@ class DeviceRatings:
         self.item_chunks = max(1, min(int(item_chunks), self.n_items)) if self.world > 1 else 1
         n_own = self.user_hi - self.user_lo
         env = lambda k: int(os.environ[k]) if os.environ.get(k) else None
-        self.item_tile_bounds = tile_bounds(0, self.n_items, row_bytes, tile_bytes,
-                                            user_pass_tiles if user_pass_tiles is not None else env("PMF_USER_PASS_TILES"))
+        upt = user_pass_tiles if user_pass_tiles is not None else env("PMF_USER_PASS_TILES")
+        if self.world > 1 and upt is None:
+            # several GPUs: the user pass is tiled over the item chunks, so that tile c of the NEXT sweep's user pass only
+            # needs the combine of chunk c to be complete (the combines of the later chunks overlap it)
+            from .parallel import item_chunk_bounds
+            self.item_tile_bounds = np.asarray(item_chunk_bounds(self.n_items, self.item_chunks), dtype=np.int64)
+        else:
+            self.item_tile_bounds = tile_bounds(0, self.n_items, row_bytes, tile_bytes, upt)
         self.user_tile_bounds = tile_bounds(self.user_lo, self.user_hi, row_bytes, tile_bytes,
                                             item_pass_tiles if item_pass_tiles is not None else env("PMF_ITEM_PASS_TILES"))
         launches_u = len(self.item_tile_bounds) - 1
