@@ -65,19 +65,32 @@ def balanced_bounds_from_counts(counts, parts):
     return balanced_row_bounds(row_ptr, parts)
 
 
-def item_chunk_bounds(n_items, chunks):
-    """Item-row chunks of the multi-GPU sweep, in processing order: `chunks` equal ranges (int list, chunks+1 entries).
+def item_chunk_bounds(n_items, chunks, shape=None):
+    """Item-row chunks of the multi-GPU sweep, in processing order (int list, chunks+1 entries).
 
-    The item pass parks its row sums chunk by chunk; the cross-rank combine of chunk c (side stream) overlaps the pass over
-    the later chunks and -- the user pass being tiled over the SAME item ranges -- the next sweep's user-pass tiles < c."""
+    The item pass parks its row sums chunk by chunk; the cross-rank combine of chunk c (high-priority side stream)
+    overlaps the pass over the later chunks.  shape "equal": equal ranges -- with the user pass tiled over the SAME ranges
+    the combines also overlap the next sweep's user-pass tiles;  "shrink": sizes proportional to chunks, chunks-1, ..., 1,
+    so that the last chunk's combine -- the only one nothing overlaps when the user pass is not tiled -- is the smallest
+    (40/30/20/10 % for 4 chunks).  Default: PMF_CHUNK_SHAPE or "shrink"."""
     chunks = max(1, min(int(chunks), int(n_items)))
-    return [n_items * c // chunks for c in range(chunks + 1)]
+    shape = shape or os.environ.get("PMF_CHUNK_SHAPE", "shrink")
+    if shape == "equal":
+        return [n_items * c // chunks for c in range(chunks + 1)]
+    total = chunks * (chunks + 1) // 2
+    bounds, acc = [0], 0
+    for c in range(chunks):
+        acc += chunks - c
+        bounds.append(max(bounds[-1] + 1, n_items * acc // total) if c < chunks - 1 else n_items)
+    for c in range(chunks - 1, 0, -1):          # tiny inputs: keep every chunk non-empty
+        bounds[c] = min(bounds[c], bounds[c + 1] - 1)
+    return bounds
 
 
-def owned_item_ranges(n_items, chunks, world, rank):
+def owned_item_ranges(n_items, chunks, world, rank, shape=None):
     """Item rows whose combine step `rank` performs: the rank's share of each chunk of item_chunk_bounds()
     (inside a chunk rank r owns the r-th of `world` equal parts)."""
-    b = item_chunk_bounds(n_items, chunks)
+    b = item_chunk_bounds(n_items, chunks, shape)
     out = []
     for c in range(len(b) - 1):
         lo, n = b[c], b[c + 1] - b[c]

@@ -94,13 +94,15 @@ def test_item_chunks_and_owned_ranges_partition_the_items():
     """Multi-GPU item pass: chunks (processing order) x ranks tile [0, n_items) exactly once."""
     from prob_matrix_factorization_b200.parallel import item_chunk_bounds, owned_item_ranges
     for n_items, chunks, world in [(500_000, 4, 8), (10, 4, 3), (3, 4, 2), (7, 1, 8), (12_000, 3, 4), (5, 8, 8)]:
-        b = item_chunk_bounds(n_items, chunks)
+        be = item_chunk_bounds(n_items, chunks, "equal")
+        assert max(np.diff(be)) - min(np.diff(be)) <= 1 and be[0] == 0 and be[-1] == n_items
+        b = item_chunk_bounds(n_items, chunks, "shrink")
         assert b[0] == 0 and b[-1] == n_items and all(x < y for x, y in zip(b, b[1:]))
         sizes = [y - x for x, y in zip(b, b[1:])]
-        assert max(sizes) - min(sizes) <= 1
+        assert sizes == sorted(sizes, reverse=True) or n_items < 20          # the exposed (last) chunk is the smallest
         seen = np.zeros(n_items, dtype=np.int32)
         for r in range(world):
-            ranges = owned_item_ranges(n_items, chunks, world, r)
+            ranges = owned_item_ranges(n_items, chunks, world, r, "shrink")
             assert len(ranges) == len(b) - 1
             for c, (lo, hi) in enumerate(ranges):
                 assert b[c] <= lo <= hi <= b[c + 1]
