@@ -644,9 +644,11 @@ def run_cavi(job, name):
             "config": {"workload": describe(w, name),
                        "sharding": ("ratings by nonzero along nnz-balanced user ranges; E_theta rows live with their owner, "
                                     "E_beta replicated") if world > 1 else "single GPU",
-                       "combine": {"mc": "item pass: per-rank row sums added in the NVSwitch (multimem.ld_reduce) by the row's "
-                                         "owner, Gamma update, new rows replicated with multimem.st; item rows in "
-                                         f"{eng.item_chunks} chunks, the combine of a chunk overlaps the pass over the next",
+                       "combine": {"mc": ("item pass: per-rank row sums staged on the row's owner by the copy engines, added in rank order"
+                                          if getattr(eng, "staged", False) else
+                                          "item pass: per-rank row sums added in the NVSwitch (multimem.ld_reduce) by the row's owner")
+                                         + f", Gamma update, new rows replicated with multimem.st; item rows in {eng.item_chunks} "
+                                         "chunks, the exchange of a chunk overlaps the pass over the next",
                                    "nccl": "item pass: NCCL all-reduce of the row sums, every rank updates every row",
                                    "none": None}[eng.exchange],
                        "tiles": {"user_pass": len(eng.r.user_tiles), "item_pass": len(eng.r.item_tiles)},
@@ -856,7 +858,7 @@ def main():
     ap.add_argument("--no-fit-df", action="store_true", help="skip the fit(DataFrame) end-to-end leg")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--dense-adam", action="store_true", help="c4: dense Adam instead of the lazy (touch-only) one")
-    ap.add_argument("--exchange", default=None, choices=["nccl", "mc"], help="multi-GPU combine of the item pass (default mc)")
+    ap.add_argument("--exchange", default=None, choices=["nccl", "mc", "ce"], help="multi-GPU combine of the item pass (default: PMF_EXCHANGE or the library's)")
     ap.add_argument("--tune", default="", help="comma list key=value passed to pmf_tune (experiments)")
     args = ap.parse_args()
     claim_stdout()

@@ -42,6 +42,9 @@ int pmf_copy_to_host(void* h_dst, const void* d_src, int64_t bytes, void* stream
 /* Kernel-variant selection for experiments ("gamma_group", "gamma_unroll"; 0 = automatic).  Process-wide and not
  * synchronised: set before launching work, never while another thread is inside the library. */
 int pmf_tune(const char* key, int value);
+/* Asynchronous copy between device buffers by the copy engines (cudaMemcpyAsync, unified addressing: a pointer may be a
+ * peer GPU's memory mapped into this process) -- used to stage per-rank row sums on their owner without occupying SMs. */
+int pmf_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
 /* Return the library's cached (freed but retained) device memory of the current device to the driver.  The library
  * allocates rating lists and scratch from its own stream-ordered pool (it never changes the default pool's settings)
  * and keeps up to PMF_POOL_KEEP_MB (default 8192) MB across fits.  Synchronises the device. */
@@ -149,6 +152,19 @@ int pmf_gamma_combine(int32_t row_begin, int32_t row_end, int32_t K, int32_t ld,
                       const float* d_mc_acc, int32_t acc_row_base, float* d_E_self, float* d_mc_E_self, float* d_shp,
                       float* d_rte, float shape_prior, float rate_prior, const float* d_rate_prior_vec,
                       float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior, void* stream);
+
+/* The same combine with the ranks' row sums STAGED in local memory: every rank copies, with the copy engines (no SMs, so
+ * the transfers overlap the pass kernels of the next item chunk), the sums of the rows another rank owns into that rank's
+ * staging table d_stage[n_src][src_stride floats] (slot s = source rank s; row q of a slot = the owner's q-th row,
+ * 2*ld floats).  For rows [row_begin,row_end) -- slot rows stage_row0 .. -- the sums are added in rank order, the local
+ * ones (d_acc) taking slot self_rank's place, so the result is deterministic and independent of the owner; update and
+ * replication as in pmf_gamma_combine. */
+int pmf_gamma_combine_staged(int32_t row_begin, int32_t row_end, int32_t K, int32_t ld, const float* d_acc,
+                             int32_t acc_row_base, const float* d_stage, int32_t n_src, int64_t src_stride,
+                             int32_t self_rank, int32_t stage_row0, float* d_E_self, float* d_mc_E_self, float* d_shp,
+                             float* d_rte, float shape_prior, float rate_prior, const float* d_rate_prior_vec,
+                             float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior,
+                             void* stream);
 
 /* Extended Poisson MF (poisson_mf_extended_cavi.py:110-164 user side, :169-216 item side):
  * x_ui ~ Poisson(phi_u psi_i theta_u . beta_i).  One pass over the rows of `csr`:

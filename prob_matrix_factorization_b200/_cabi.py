@@ -59,6 +59,7 @@ _PROTOTYPES = {
     "pmf_coo_partition": (C.c_int, [VP, VP, VP, C.c_int64, C.c_int32, c_i32p, C.c_int32, VP, VP, VP,
                                     C.POINTER(C.c_int64), VP]),
     "pmf_trim": (C.c_int, []),
+    "pmf_memcpy_async": (C.c_int, [VP, VP, C.c_int64, VP]),
     "pmf_loop_begin": (C.c_int, [VP, C.POINTER(VP)]),
     "pmf_loop_decide": (C.c_int, [VP, VP, C.c_int32, C.c_double, C.c_int32, C.c_int32, VP, VP, VP]),
     "pmf_loop_end": (C.c_int, [VP]),
@@ -83,6 +84,9 @@ _PROTOTYPES = {
                                      VP, VP, C.c_float, C.c_float, VP, VP, C.c_int32, C.c_int32, VP]),
     "pmf_gamma_combine": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, VP, VP, C.c_int32, VP, VP, VP, VP,
                                     C.c_float, C.c_float, VP, VP, VP, C.c_float, C.c_float, VP]),
+    "pmf_gamma_combine_staged": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, VP, C.c_int32, VP, C.c_int32, C.c_int64,
+                                           C.c_int32, C.c_int32, VP, VP, VP, VP, C.c_float, C.c_float, VP, VP, VP, C.c_float,
+                                           C.c_float, VP]),
     "pmf_gamma_pass_ext": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP, VP, VP, VP, VP, VP, VP, C.c_float, C.c_float, VP, VP]),
     "pmf_scale_rows": (C.c_int, [VP, VP, C.c_int64, C.c_int32, VP, VP]),
     "pmf_gamma_geomean": (C.c_int, [VP, VP, C.c_int64, C.c_int32, C.c_int32, VP, VP]),

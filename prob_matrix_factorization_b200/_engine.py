@@ -292,12 +292,15 @@ class GammaEngine:
         f = lambda rows, cols=self.ld: torch.zeros((rows, cols), dtype=torch.float32, device=self.dev)
         if exchange is None:
             exchange = os.environ.get("PMF_EXCHANGE", "mc")
-        if exchange not in ("mc", "nccl"):
-            raise ValueError("exchange must be 'mc' or 'nccl'")
+        if exchange not in ("mc", "ce", "nccl"):
+            raise ValueError("exchange must be 'mc', 'ce' or 'nccl'")
         self.exchange = exchange if self.world > 1 else "none"
         self._symm = {}
         self._side = None
         self._ready = None        # events of an item pass whose combines are still in flight (see item_pass(join=False))
+        self.staged = self.exchange == "ce"      # "ce": sums staged on their owner by the copy engines (else in-switch reduce)
+        if self.exchange == "ce":
+            self.exchange = "mc"                 # same protocol (barriers, chunks, multicast replication of the new rows)
         if self.exchange == "mc":
             import torch.distributed as dist
             ok, why = 1.0, ""
@@ -320,6 +323,7 @@ class GammaEngine:
         if self.exchange == "mc":
             self.E_beta, self.acc_item = self._symm["E_beta"][0], self._symm["acc_item"][0]
             self._side = side_stream(self.dev, "combine", high_priority=True)
+            self._copy_streams = [side_stream(self.dev, f"copy{k}") for k in range(3)] if self.staged else []
         else:
             self.E_beta = f(self.M)
             self.acc_item = f(self.M, 2 * self.ld) if (self.world > 1 or n_item_tiles > 1) else None
@@ -412,9 +416,43 @@ class GammaEngine:
                    hyper_rate_prior, _cabi.ptr(ws), _cabi.ptr(acc) if flags else None, acc_base, flags,
                    _cabi.stream_ptr())
 
-    def _combine(self, lo, hi, write_params, multicast):
+    def _stage_copies(self, c, done):
+        """Chunk c: copy the sums of the rows each peer owns into that peer's staging table (copy engines; no SMs)."""
+        stage, hdl = self._symm["stage"][0], self._symm["stage"][1]
+        if not hasattr(self, "_peer_stage"):
+            self._peer_stage = {p: hdl.get_buffer(p, tuple(stage.shape), torch.float32) for p in range(self.world) if p != self.rank}
+            C_ = self.item_chunks
+            self._owned_all = {p: owned_item_ranges(self.M, C_, self.world, p) for p in range(self.world)}
+            self._row0_all = {p: np.concatenate([[0], np.cumsum([hi - lo for lo, hi in self._owned_all[p]])]) for p in range(self.world)}
+        row_bytes = 2 * self.ld * 4
+        events = []
+        for k, cs in enumerate(self._copy_streams):
+            cs.wait_event(done)
+            for p in range(self.world):
+                if p == self.rank or (p % len(self._copy_streams)) != k:
+                    continue
+                lo, hi = self._owned_all[p][c]
+                if hi > lo:
+                    dst = self._peer_stage[p][self.rank, int(self._row0_all[p][c])]
+                    _cabi.call("pmf_memcpy_async", dst.data_ptr(), self.acc_item[lo].data_ptr(), (hi - lo) * row_bytes, cs.cuda_stream)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            events.append(ev)
+        return events
+
+    def _combine(self, lo, hi, write_params, multicast, chunk=0):
         h = self.hyper
         wp = write_params and self.keep_params
+        if multicast and self.staged:
+            stage = self._symm["stage"][0]
+            _cabi.call("pmf_gamma_combine_staged", lo, hi, self.K, self.ld, self.acc_item.data_ptr(), 0, stage.data_ptr(),
+                       self.world, self._stage_rows * 2 * self.ld, self.rank, int(self._row0_all[self.rank][chunk]),
+                       self.E_beta.data_ptr(), self._symm["E_beta"][2],
+                       _cabi.ptr(self.shp_beta if wp else None), _cabi.ptr(self.rte_beta if wp else None),
+                       self.item_shape, 0.0 if self.item_rate is None else self.item_rate, _cabi.ptr(self.E_eta),
+                       _cabi.ptr(self.rate_eta), _cabi.ptr(self.E_eta), h["item_shape"] if h else 0.0,
+                       h["item_rate_prior"] if h else 0.0, _cabi.stream_ptr())
+            return
         _cabi.call("pmf_gamma_combine", lo, hi, self.K, self.ld, self.acc_item.data_ptr(),
                    self._symm["acc_item"][2] if multicast else None, 0, self.E_beta.data_ptr(),
                    self._symm["E_beta"][2] if multicast else None,
@@ -428,7 +466,12 @@ class GammaEngine:
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         group = dist.group.WORLD
-        for name, shape in (("E_beta", (self.M, self.ld)), ("acc_item", (self.M, 2 * self.ld))):
+        tables = [("E_beta", (self.M, self.ld)), ("acc_item", (self.M, 2 * self.ld))]
+        if self.staged:
+            # staging table: slot s = the sums rank s computed for the rows THIS rank owns (owner's rows in chunk order)
+            self._stage_rows = -(-self.M // self.world) + 64       # a rank owns M/world rows, +-1 per chunk
+            tables.append(("stage", (self.world, self._stage_rows, 2 * self.ld)))
+        for name, shape in tables:
             key = (name, self.dev.index)
             hit = _SYMM_CACHE.get(key)
             if hit is not None and not hit["busy"] and tuple(hit["t"].shape) == shape and hit["group"] == group.group_name:
@@ -437,10 +480,10 @@ class GammaEngine:
                 continue
             t = symm_mem.empty(shape, dtype=torch.float32, device=self.dev)
             hdl = symm_mem.rendezvous(t, group.group_name)
-            if not hdl.multicast_ptr:
+            if not hdl.multicast_ptr and name != "stage":
                 raise RuntimeError("no multicast pointer")
             t.zero_()
-            entry = {"t": t, "hdl": hdl, "mc": int(hdl.multicast_ptr), "group": group.group_name, "busy": True}
+            entry = {"t": t, "hdl": hdl, "mc": int(hdl.multicast_ptr or 0), "group": group.group_name, "busy": True}
             if hit is None or not hit["busy"]:
                 _SYMM_CACHE[key] = entry          # (an entry in use by a live engine is left alone; this one is not cached)
             self._symm[name] = (t, hdl, entry["mc"], entry)
@@ -497,6 +540,9 @@ class GammaEngine:
             if self.exchange == "mc":
                 done = torch.cuda.Event()
                 done.record(main)
+                if self.staged:
+                    for ev in self._stage_copies(c, done):
+                        self._side.wait_event(ev)
                 self._side.wait_event(done)
                 with torch.cuda.stream(self._side):
                     # one barrier says: every rank has parked its sums of chunk c AND finished its combine of chunk c-1
@@ -505,7 +551,7 @@ class GammaEngine:
                         ready.append(torch.cuda.Event())
                         ready[-1].record(self._side)            # E_beta rows of chunk c-1 are final on every replica
                     lo, hi = self.owned_items[c]
-                    self._combine(lo, hi, write_params, multicast=True)
+                    self._combine(lo, hi, write_params, multicast=True, chunk=c)
         if self.exchange == "mc":
             with torch.cuda.stream(self._side):
                 self._rank_barrier()                            # every rank's new E_beta rows have landed everywhere

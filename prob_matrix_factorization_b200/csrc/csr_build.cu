@@ -538,6 +538,14 @@ int pmf_copy_to_host(void* h_dst, const void* d_src, int64_t bytes, void* stream
     return PMF_OK;
 }
 
+int pmf_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream) {
+    PMF_REQUIRE(bytes >= 0 && (bytes == 0 || (dst && src)), "bad argument");
+    if (bytes == 0) return PMF_OK;
+    // unified addressing: either pointer may be a peer GPU's memory mapped into this process; the copy engines move it
+    PMF_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return PMF_OK;
+}
+
 int pmf_trim(void) {
     PMF_CUDA(cudaDeviceSynchronize());
     if (cudaMemPool_t pool = library_pool()) PMF_CUDA(cudaMemPoolTrimTo(pool, 0));

@@ -424,8 +424,18 @@ __global__ void __launch_bounds__(256) gamma_multi_kernel(const GammaArgs a) {
 // row R adds the ranks' sums -- ONE multimem.ld_reduce per 16 bytes, the addition is done by the NVSwitch -- applies the
 // Gamma update and pushes the new row to every replica with multimem.st.  With mc_acc == NULL the sums in `acc` are
 // already complete (NCCL all-reduce, or a single GPU) and are read with plain loads.  One lane group per row.
+// (staged form) n_src > 0: the ranks' sums of the row were copied by the copy engines into `stage`
+// ([n_src][src_stride floats], slot s = source rank s, row q of a slot = this owner's q-th row); they are added in rank
+// order with the local sums in slot `self_rank`'s place, so the result does not depend on who owns the row.
+struct StageArgs {
+    const float* stage;
+    int64_t src_stride;   // floats between two sources' slots
+    int32_t n_src, self_rank, row0;   // row0: slot row of row_begin
+};
+
 template <int G, int V, int MODE>
-__global__ void __launch_bounds__(256) gamma_combine_kernel(const GammaArgs a, const float* mc_acc, int row_begin, int row_end) {
+__global__ void __launch_bounds__(256) gamma_combine_kernel(const GammaArgs a, const float* mc_acc, int row_begin, int row_end,
+                                                            const StageArgs st) {
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -439,7 +449,15 @@ __global__ void __launch_bounds__(256) gamma_combine_kernel(const GammaArgs a, c
         self[v] = sa[v] = sb[v] = f4_zero();
         if (idx < a.nvec) {
             self[v] = *reinterpret_cast<const float4*>(a.E_self + (size_t)R * a.ld + idx * 4);
-            if (mc_acc) {
+            if (st.n_src > 0) {
+                const size_t q = (size_t)(st.row0 + (R - row_begin)) * 2 * a.ld;
+                for (int src = 0; src < st.n_src; ++src) {
+                    const float* base = src == st.self_rank ? a.acc + poff : st.stage + (size_t)src * st.src_stride + q;
+                    const float4 pa = ld_stream_f4(base + idx * 4), pb = ld_stream_f4(base + a.ld + idx * 4);
+                    sa[v].x += pa.x; sa[v].y += pa.y; sa[v].z += pa.z; sa[v].w += pa.w;
+                    sb[v].x += pb.x; sb[v].y += pb.y; sb[v].z += pb.z; sb[v].w += pb.w;
+                }
+            } else if (mc_acc) {
                 asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
                              : "=f"(sa[v].x), "=f"(sa[v].y), "=f"(sa[v].z), "=f"(sa[v].w) : "l"(mc_acc + poff + idx * 4) : "memory");
                 asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -541,10 +559,11 @@ static int dispatch_gamma(const GammaArgs& a, int mode, cudaStream_t s) {
 }
 
 template <int G, int V>
-static int launch_combine(const GammaArgs& a, const float* mc_acc, int row_begin, int row_end, int mode, cudaStream_t s) {
+static int launch_combine(const GammaArgs& a, const float* mc_acc, int row_begin, int row_end, int mode, cudaStream_t s,
+                          const StageArgs& st) {
     const unsigned grid = (unsigned)cdiv((int64_t)(row_end - row_begin) * G, 256);
-    if (mode == 1) gamma_combine_kernel<G, V, 1><<<grid, 256, 0, s>>>(a, mc_acc, row_begin, row_end);
-    else gamma_combine_kernel<G, V, 0><<<grid, 256, 0, s>>>(a, mc_acc, row_begin, row_end);
+    if (mode == 1) gamma_combine_kernel<G, V, 1><<<grid, 256, 0, s>>>(a, mc_acc, row_begin, row_end, st);
+    else gamma_combine_kernel<G, V, 0><<<grid, 256, 0, s>>>(a, mc_acc, row_begin, row_end, st);
     PMF_LAUNCH_CHECK();
     return PMF_OK;
 }
@@ -613,10 +632,11 @@ int pmf_gamma_pass_acc(const pmf_csr* csr, int32_t K, int32_t ld, const float* d
     return dispatch_gamma(a, d_hyper_rate != nullptr ? 1 : 0, (cudaStream_t)stream);
 }
 
-int pmf_gamma_combine(int32_t row_begin, int32_t row_end, int32_t K, int32_t ld, const float* d_acc,
-                      const float* d_mc_acc, int32_t acc_row_base, float* d_E_self, float* d_mc_E_self, float* d_shp,
-                      float* d_rte, float shape_prior, float rate_prior, const float* d_rate_prior_vec,
-                      float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior, void* stream) {
+static int combine_impl(int32_t row_begin, int32_t row_end, int32_t K, int32_t ld, const float* d_acc,
+                        const float* d_mc_acc, int32_t acc_row_base, float* d_E_self, float* d_mc_E_self, float* d_shp,
+                        float* d_rte, float shape_prior, float rate_prior, const float* d_rate_prior_vec,
+                        float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior,
+                        const StageArgs& st, void* stream) {
     PMF_TRY(check_gamma_tables(K, ld, d_acc, d_E_self, d_hyper_rate, d_hyper_mean));
     PMF_REQUIRE(0 <= acc_row_base && acc_row_base <= row_begin && row_begin <= row_end, "bad row range [%d,%d) base %d",
                 row_begin, row_end, acc_row_base);
@@ -632,12 +652,36 @@ int pmf_gamma_combine(int32_t row_begin, int32_t row_end, int32_t K, int32_t ld,
     const int mode = d_hyper_rate != nullptr ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     const int nv = a.nvec;
-    if (nv <= 4) return launch_combine<4, 1>(a, d_mc_acc, row_begin, row_end, mode, s);
-    if (nv <= 8) return launch_combine<8, 1>(a, d_mc_acc, row_begin, row_end, mode, s);
-    if (nv <= 16) return launch_combine<8, 2>(a, d_mc_acc, row_begin, row_end, mode, s);
-    if (nv <= 24) return launch_combine<8, 3>(a, d_mc_acc, row_begin, row_end, mode, s);
-    if (nv <= 32) return launch_combine<8, 4>(a, d_mc_acc, row_begin, row_end, mode, s);
-    return launch_combine<16, 4>(a, d_mc_acc, row_begin, row_end, mode, s);
+    if (nv <= 4) return launch_combine<4, 1>(a, d_mc_acc, row_begin, row_end, mode, s, st);
+    if (nv <= 8) return launch_combine<8, 1>(a, d_mc_acc, row_begin, row_end, mode, s, st);
+    if (nv <= 16) return launch_combine<8, 2>(a, d_mc_acc, row_begin, row_end, mode, s, st);
+    if (nv <= 24) return launch_combine<8, 3>(a, d_mc_acc, row_begin, row_end, mode, s, st);
+    if (nv <= 32) return launch_combine<8, 4>(a, d_mc_acc, row_begin, row_end, mode, s, st);
+    return launch_combine<16, 4>(a, d_mc_acc, row_begin, row_end, mode, s, st);
+}
+
+int pmf_gamma_combine(int32_t row_begin, int32_t row_end, int32_t K, int32_t ld, const float* d_acc,
+                      const float* d_mc_acc, int32_t acc_row_base, float* d_E_self, float* d_mc_E_self, float* d_shp,
+                      float* d_rte, float shape_prior, float rate_prior, const float* d_rate_prior_vec,
+                      float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior, void* stream) {
+    const StageArgs st = {nullptr, 0, 0, 0, 0};
+    return combine_impl(row_begin, row_end, K, ld, d_acc, d_mc_acc, acc_row_base, d_E_self, d_mc_E_self, d_shp, d_rte,
+                        shape_prior, rate_prior, d_rate_prior_vec, d_hyper_rate, d_hyper_mean, hyper_shape,
+                        hyper_rate_prior, st, stream);
+}
+
+int pmf_gamma_combine_staged(int32_t row_begin, int32_t row_end, int32_t K, int32_t ld, const float* d_acc,
+                             int32_t acc_row_base, const float* d_stage, int32_t n_src, int64_t src_stride,
+                             int32_t self_rank, int32_t stage_row0, float* d_E_self, float* d_mc_E_self, float* d_shp,
+                             float* d_rte, float shape_prior, float rate_prior, const float* d_rate_prior_vec,
+                             float* d_hyper_rate, float* d_hyper_mean, float hyper_shape, float hyper_rate_prior,
+                             void* stream) {
+    PMF_REQUIRE(d_stage != nullptr && n_src >= 1 && n_src <= 64 && self_rank >= 0 && self_rank < n_src && stage_row0 >= 0 &&
+                    src_stride >= 0, "bad staging arguments");
+    const StageArgs st = {d_stage, src_stride, n_src, self_rank, stage_row0};
+    return combine_impl(row_begin, row_end, K, ld, d_acc, nullptr, acc_row_base, d_E_self, d_mc_E_self, d_shp, d_rte,
+                        shape_prior, rate_prior, d_rate_prior_vec, d_hyper_rate, d_hyper_mean, hyper_shape,
+                        hyper_rate_prior, st, stream);
 }
 
 int pmf_gamma_pass_ext(const pmf_csr* csr, int32_t K, int32_t ld, const float* d_E_oth, const float* d_scale_oth,

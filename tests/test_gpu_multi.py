@@ -1,5 +1,5 @@
-"""Row (e): ratings sharded by user range over 2 / 4 / 8 GPUs; multicast (in-switch) and NCCL combine of the item
-pass's row sums.  Results equal the oracle and every rank ends with bit-identical replicated tables.  Each world size is
+"""Row (e): ratings sharded by user range over 2 / 4 / 8 GPUs; in-switch ("mc"), copy-engine staged ("ce") and NCCL
+combine of the item pass's row sums.  Results equal the oracle and every rank ends with bit-identical replicated tables.  Each world size is
 skipped on boxes with fewer GPUs."""
 import os
 import subprocess
@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("exchange", ["mc", "nccl"])
+@pytest.mark.parametrize("exchange", ["mc", "ce", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_fit_matches_oracle(world, exchange):
     if torch.cuda.device_count() < world:
