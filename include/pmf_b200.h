@@ -297,6 +297,21 @@ int pmf_gauss_factor_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, c
 int pmf_gauss_bias_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_m_self,
                         const float* d_b_oth, float* d_b_self, float sigma2, float eta_b2, void* d_workspace, void* stream);
 
+/* Sharded forms (several GPUs, ratings sharded along user ranges; SURVEY.md §8e "Gaussian shards identically"): the rows of
+ * `csr` get ratings from every rank, so the pass is split around the caller's NCCL all-reduce of the row statistics.
+ *   phase 1: accumulate this rank's ratings into d_row_sums[n_rows][ldq + ld] (factor pass; packed second moments |
+ *            residual-weighted means) or d_row_resid[n_rows] (bias pass, float64);
+ *   (caller: all-reduce SUM over the ranks)
+ *   phase 2: the row update of pmf_gauss_factor_pass / pmf_gauss_bias_pass from those sums; d_counts[n_rows] = ratings of
+ *            each row over ALL ranks (rows with none keep their state; the bias precision uses it). */
+int pmf_gauss_factor_pass_sharded(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_Q_oth,
+                                  const float* d_b_oth, float* d_m_self, float* d_V_self, float* d_Q_self,
+                                  const float* d_b_self, float sigma2, float eta2, void* d_workspace, float* d_row_sums,
+                                  const int32_t* d_counts, int32_t phase, void* stream);
+int pmf_gauss_bias_pass_sharded(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_m_self,
+                                const float* d_b_oth, float* d_b_self, float sigma2, float eta_b2, void* d_workspace,
+                                double* d_row_resid, const int32_t* d_counts, int32_t phase, void* stream);
+
 /* ---- a6/a7: gradient-based HPF (HPF_PyTorch) ----------------------------------------------
  * Parameters keep the reference's shapes (hpf_pytorch.py:39-48): theta_raw (N,K), beta_raw (M,K) row-major
  * with row stride K, xi_raw (N), eta_raw (M), all float32 and unconstrained (softplus applied inside).

@@ -101,6 +101,9 @@ _PROTOTYPES = {
     "pmf_gauss_workspace_bytes": (C.c_int64, [VP, C.c_int32]),
     "pmf_gauss_factor_pass": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, VP, VP, C.c_float, C.c_float, VP, VP]),
     "pmf_gauss_bias_pass": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, C.c_float, C.c_float, VP, VP]),
+    "pmf_gauss_factor_pass_sharded": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, VP, VP, C.c_float, C.c_float, VP, VP, VP,
+                                                C.c_int32, VP]),
+    "pmf_gauss_bias_pass_sharded": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, C.c_float, C.c_float, VP, VP, VP, C.c_int32, VP]),
     "pmf_hpf_map_loss_grad": (C.c_int, [VP, VP, C.c_int32, VP, C.c_int64, VP, VP, VP, VP, VP, VP, C.c_int32, C.c_int32,
                                         C.c_int32] + [C.c_float] * 6 + [VP, VP, VP, VP, VP, VP, VP]),
     "pmf_adam_dense_step": (C.c_int, [VP, VP, VP, VP, C.c_int64] + [C.c_float] * 5 + [VP]),

@@ -92,9 +92,8 @@ class EvalSet:
         u32, i32 = normalise_ids(users, n_users), normalise_ids(items, n_items)
         labels_all = None
         if self.sharded:
-            if drop_invalid:
-                raise NotImplementedError("sharded evaluation with drop_invalid")
-            labels_all = np.unique(y)                       # labels are those of the WHOLE frame on every rank
+            # labels are those of the WHOLE frame on every rank (of its rows with seen ids when those are dropped)
+            labels_all = np.unique(y[(u32 < n_users) & (i32 < n_items)] if drop_invalid else y)
             lo, hi, is_last = user_range
             uc = np.minimum(u32, n_users)
             keep = (uc >= lo) & ((uc < hi) | bool(is_last))

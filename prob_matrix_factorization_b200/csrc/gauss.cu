@@ -31,7 +31,27 @@ struct GaussArgs {
     float *m_self, *V_self, *Q_self;
     float sigma2, eta2;
     float* scratch;  // [n_seg][ldq + ld]
+    // sharded form (several GPUs): the segment sums are first added per row into row_sums[n_rows][ldq + ld], summed over
+    // the ranks by the caller (NCCL all-reduce: the per-iteration "sufficient statistics combine" of SURVEY.md §8e) and
+    // the solve then reads them; counts[n_rows] = ratings of the row over ALL ranks (the skip rule :134-135)
+    float* row_sums;
+    const int32_t* counts;
 };
+
+// row_sums[row] = sum of the row's segment sums, in segment order (one thread per float4 slot)
+__global__ void gauss_row_sums_kernel(const GaussArgs a) {
+    const int W4 = a.nq4 + a.nm4;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)a.n_rows * W4) return;
+    const int row = (int)(e / W4), slot = (int)(e % W4);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sg = a.row_seg[row]; sg < a.row_seg[row + 1]; ++sg) {
+        if (a.row_ptr[row + 1] == a.row_ptr[row]) break;     // an empty row's single segment was never written
+        const float4 v = *reinterpret_cast<const float4*>(a.scratch + (size_t)sg * (a.ldq + a.ld) + 4 * slot);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(a.row_sums + (size_t)row * (a.ldq + a.ld) + 4 * slot) = acc;
+}
 
 template <int V>
 __global__ void gauss_accumulate_kernel(const GaussArgs a) {
@@ -96,20 +116,21 @@ __global__ void __launch_bounds__(256) gauss_solve_kernel(const GaussArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= a.n_rows) return;
-    if (a.row_ptr[row + 1] == a.row_ptr[row]) return;  // no ratings: keep the state (:134-135)
+    if (a.counts ? a.counts[row] == 0 : a.row_ptr[row + 1] == a.row_ptr[row]) return;  // no ratings: keep the state (:134-135)
     double* A = sm + (size_t)warp * ((size_t)K * LD + 3 * K);
     double* rinv = A + (size_t)K * LD;
     double* rhs = rinv + K;
     double* mean = rhs + K;
-    const int s0 = a.row_seg[row], s1 = a.row_seg[row + 1];
     const int W = a.ldq + a.ld;
+    const int s0 = a.row_sums ? row : a.row_seg[row], s1 = a.row_sums ? row + 1 : a.row_seg[row + 1];
+    const float* sums = a.row_sums ? a.row_sums : a.scratch;
     const int npk = K * (K + 1) / 2;
     const double inv_sigma2 = 1.0 / (double)a.sigma2, inv_eta2 = 1.0 / (double)a.eta2;
     // P = I/eta2 + S/sigma2 (lower triangle), rhs = sum res*m; the segments' sums are added in segment order
     for (int e = lane; e < npk + K; e += 32) {
         const int off = e < npk ? e : a.ldq + (e - npk);
         double s = 0.0;
-        for (int sg = s0; sg < s1; ++sg) s += (double)a.scratch[(size_t)sg * W + off];
+        for (int sg = s0; sg < s1; ++sg) s += (double)sums[(size_t)sg * W + off];
         if (e < npk) {
             int i, j;
             unpack_tri(e, i, j);
@@ -193,6 +214,9 @@ struct BiasArgs {
     float* b_self;
     float sigma2, eta_b2;
     double* partial;   // [n_seg]
+    double* row_resid;         // sharded form: per-row residual sums (summed over the ranks by the caller) ...
+    const int32_t* counts;     // ... and the rows' rating counts over all ranks
+    int phase;                 // 0 whole pass, 1 up to the row sums, 2 from the (all-reduced) row sums
 };
 
 __global__ void __launch_bounds__(256) gauss_bias_partial_kernel(const BiasArgs a) {
@@ -229,10 +253,17 @@ __global__ void __launch_bounds__(256) gauss_bias_partial_kernel(const BiasArgs 
 __global__ void __launch_bounds__(256) gauss_bias_finish_kernel(const BiasArgs a) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= a.n_rows) return;
-    const int n = a.row_ptr[row + 1] - a.row_ptr[row];
-    if (n == 0) return;  // gaussian_mf_cavi_bias.py:208-209
+    const int n_local = a.row_ptr ? a.row_ptr[row + 1] - a.row_ptr[row] : 0;
     double acc = 0.0;
-    for (int sg = a.row_seg[row]; sg < a.row_seg[row + 1]; ++sg) acc += a.partial[sg];
+    if (a.phase != 2) {
+        if (n_local > 0)
+            for (int sg = a.row_seg[row]; sg < a.row_seg[row + 1]; ++sg) acc += a.partial[sg];
+        if (a.phase == 1) { a.row_resid[row] = acc; return; }
+    } else {
+        acc = a.row_resid[row];
+    }
+    const int n = a.counts ? a.counts[row] : n_local;
+    if (n == 0) return;  // gaussian_mf_cavi_bias.py:208-209
     const double prec = 1.0 / (double)a.eta_b2 + (double)n / (double)a.sigma2;          // :226
     a.b_self[a.row_offset + row] = (float)((1.0 / prec) / (double)a.sigma2 * acc);     // :230
 }
@@ -253,9 +284,31 @@ int64_t pmf_gauss_workspace_bytes(const pmf_csr* csr, int32_t K) {
     return b > 0 ? b : 16;
 }
 
+static int gauss_factor_impl(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_Q_oth,
+                             const float* d_b_oth, float* d_m_self, float* d_V_self, float* d_Q_self,
+                             const float* d_b_self, float sigma2, float eta2, void* d_workspace, float* d_row_sums,
+                             const int32_t* d_counts, int phase, void* stream);
+
 int pmf_gauss_factor_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_Q_oth,
                           const float* d_b_oth, float* d_m_self, float* d_V_self, float* d_Q_self,
                           const float* d_b_self, float sigma2, float eta2, void* d_workspace, void* stream) {
+    return gauss_factor_impl(csr, K, d_m_oth, d_Q_oth, d_b_oth, d_m_self, d_V_self, d_Q_self, d_b_self, sigma2, eta2,
+                             d_workspace, nullptr, nullptr, 0, stream);
+}
+
+int pmf_gauss_factor_pass_sharded(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_Q_oth,
+                                  const float* d_b_oth, float* d_m_self, float* d_V_self, float* d_Q_self,
+                                  const float* d_b_self, float sigma2, float eta2, void* d_workspace, float* d_row_sums,
+                                  const int32_t* d_counts, int32_t phase, void* stream) {
+    PMF_REQUIRE(d_row_sums != nullptr && d_counts != nullptr && (phase == 1 || phase == 2), "bad sharded-pass arguments");
+    return gauss_factor_impl(csr, K, d_m_oth, d_Q_oth, d_b_oth, d_m_self, d_V_self, d_Q_self, d_b_self, sigma2, eta2,
+                             d_workspace, d_row_sums, d_counts, phase, stream);
+}
+
+static int gauss_factor_impl(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_Q_oth,
+                             const float* d_b_oth, float* d_m_self, float* d_V_self, float* d_Q_self,
+                             const float* d_b_self, float sigma2, float eta2, void* d_workspace, float* d_row_sums,
+                             const int32_t* d_counts, int phase, void* stream) {
     PMF_REQUIRE(csr != nullptr, "csr is NULL");
     PMF_REQUIRE(K >= 1 && K <= 96, "K=%d outside [1, 96] for the Gaussian model", K);
     PMF_REQUIRE(d_m_oth && d_Q_oth && d_m_self && d_V_self && d_Q_self && d_workspace, "NULL table");
@@ -270,8 +323,9 @@ int pmf_gauss_factor_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, c
     a.m_oth = d_m_oth; a.Q_oth = d_Q_oth; a.b_oth = d_b_oth; a.b_self = d_b_self;
     a.m_self = d_m_self; a.V_self = d_V_self; a.Q_self = d_Q_self;
     a.sigma2 = sigma2; a.eta2 = eta2; a.scratch = (float*)d_workspace;
+    a.row_sums = d_row_sums; a.counts = d_counts;
     cudaStream_t s = (cudaStream_t)stream;
-    if (c.n_seg > 0) {
+    if (c.n_seg > 0 && phase != 2) {
         const int nslots = a.nq4 + a.nm4;
         // threads per segment: a multiple of 32 covering the slots with at most 4 per thread
         int V = 1;
@@ -282,6 +336,13 @@ int pmf_gauss_factor_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, c
         else if (V == 2) gauss_accumulate_kernel<2><<<c.n_seg, T, 0, s>>>(a);
         else gauss_accumulate_kernel<4><<<c.n_seg, T, 0, s>>>(a);
         PMF_LAUNCH_CHECK();
+    }
+    if (phase == 1) {
+        if (c.n_rows > 0) {
+            gauss_row_sums_kernel<<<(unsigned)cdiv((int64_t)c.n_rows * (a.nq4 + a.nm4), 256), 256, 0, s>>>(a);
+            PMF_LAUNCH_CHECK();
+        }
+        return PMF_OK;
     }
     if (c.n_rows > 0) {
         const size_t per_warp = ((size_t)K * (K + 1) + 3 * (size_t)K) * sizeof(double);
@@ -296,8 +357,25 @@ int pmf_gauss_factor_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, c
     return PMF_OK;
 }
 
+static int gauss_bias_impl(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_m_self, const float* d_b_oth,
+                           float* d_b_self, float sigma2, float eta_b2, void* d_workspace, double* d_row_resid,
+                           const int32_t* d_counts, int phase, void* stream);
+
 int pmf_gauss_bias_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_m_self,
                         const float* d_b_oth, float* d_b_self, float sigma2, float eta_b2, void* d_workspace, void* stream) {
+    return gauss_bias_impl(csr, K, d_m_oth, d_m_self, d_b_oth, d_b_self, sigma2, eta_b2, d_workspace, nullptr, nullptr, 0, stream);
+}
+
+int pmf_gauss_bias_pass_sharded(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_m_self,
+                                const float* d_b_oth, float* d_b_self, float sigma2, float eta_b2, void* d_workspace,
+                                double* d_row_resid, const int32_t* d_counts, int32_t phase, void* stream) {
+    PMF_REQUIRE(d_row_resid != nullptr && d_counts != nullptr && (phase == 1 || phase == 2), "bad sharded-pass arguments");
+    return gauss_bias_impl(csr, K, d_m_oth, d_m_self, d_b_oth, d_b_self, sigma2, eta_b2, d_workspace, d_row_resid, d_counts, phase, stream);
+}
+
+static int gauss_bias_impl(const pmf_csr* csr, int32_t K, const float* d_m_oth, const float* d_m_self, const float* d_b_oth,
+                           float* d_b_self, float sigma2, float eta_b2, void* d_workspace, double* d_row_resid,
+                           const int32_t* d_counts, int phase, void* stream) {
     PMF_REQUIRE(csr != nullptr, "csr is NULL");
     PMF_REQUIRE(K >= 1, "K must be positive");
     PMF_REQUIRE(d_m_oth && d_m_self && d_b_oth && d_b_self && d_workspace, "NULL table");
@@ -311,8 +389,9 @@ int pmf_gauss_bias_pass(const pmf_csr* csr, int32_t K, const float* d_m_oth, con
     a.m_self = d_m_self; a.m_oth = d_m_oth; a.b_oth = d_b_oth; a.b_self = d_b_self;
     a.sigma2 = sigma2; a.eta_b2 = eta_b2;
     a.partial = (double*)d_workspace;   // n_seg doubles <= pmf_gauss_workspace_bytes (>= 8 floats per segment)
+    a.row_resid = d_row_resid; a.counts = d_counts; a.phase = phase;
     cudaStream_t s = (cudaStream_t)stream;
-    if (c.n_seg > 0) {
+    if (c.n_seg > 0 && phase != 2) {
         gauss_bias_partial_kernel<<<(unsigned)cdiv((int64_t)c.n_seg * 32, 256), 256, 0, s>>>(a);
         PMF_LAUNCH_CHECK();
     }

@@ -20,6 +20,24 @@ __device__ __forceinline__ T digamma_pos(T x) {
     return r + log(x) - T(0.5) * inv - series;
 }
 
+// lgamma(s) and psi(s) together, s > 0, float64: shift to x = s + n >= 8 with the running product den = s (s+1) ... (s+n-1)
+// and num / den = sum 1/(s+i) kept as a fraction (one division at the end, no division per shift), then the Stirling /
+// asymptotic series (truncation error < 1e-12 at x = 8):
+//   lgamma(s) = lgamma(x) - log(den),  psi(s) = psi(x) - num/den.
+// Three logarithms and two divisions per call instead of libdevice's lgamma plus a division per shift: the prior /
+// entropy terms of the ELBO evaluate this pair (N + M) K times per sweep and were ~85 % of the ELBO's time.
+__device__ __forceinline__ void lgamma_digamma(double s, double& lg, double& psi) {
+    double x = s, num = 0.0, den = 1.0;
+#pragma unroll 1
+    while (x < 8.0) { num = num * x + den; den *= x; x += 1.0; }
+    const double lx = log(x), inv = 1.0 / x, inv2 = inv * inv;
+    lg = (x - 0.5) * lx - x + 0.91893853320467274178 +
+         inv * (1.0 / 12 - inv2 * (1.0 / 360 - inv2 * (1.0 / 1260 - inv2 * (1.0 / 1680 - inv2 * (1.0 / 1188)))));
+    psi = lx - 0.5 * inv -
+          inv2 * (1.0 / 12 - inv2 * (1.0 / 120 - inv2 * (1.0 / 252 - inv2 * (1.0 / 240 - inv2 * (1.0 / 132 - inv2 * (691.0 / 32760))))));
+    if (den != 1.0) { lg -= log(den); psi -= num / den; }
+}
+
 __global__ void geomean_kernel(const float* __restrict__ shp, const float* __restrict__ rte, int64_t rows, int K,
                                int ld, float* __restrict__ G) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,41 +217,48 @@ struct ElboArgs {
     double* out;
 };
 
-// likelihood part: one 8-lane group per rating (grid-stride over the local rating list, row found by search)
-__global__ void __launch_bounds__(256) elbo_like_kernel(const ElboArgs a, int64_t nnz) {
+// log(n!) for n = 0..20 (ratings are small counts: lgamma(x + 1) is a table lookup for them)
+__constant__ double kLogFactorial[21] = {
+    0.0, 0.0, 0.69314718055994530942, 1.79175946922805500081, 3.17805383034794561965, 4.78749174278204599425,
+    6.57925121201010099506, 8.52516136106541430017, 10.60460290274525022842, 12.80182748008146961121,
+    15.10441257307551529523, 17.50230784587388583929, 19.98721449566188614952, 22.55216385312342288557,
+    25.19122118273868150009, 27.89927138384089156609, 30.67186010608067280376, 33.50507345013688888401,
+    36.39544520803305357622, 39.33988418719949403622, 42.33561646075348502966};
+
+__device__ __forceinline__ double log_gamma_x_plus_1(double x) {
+    const int n = (int)x;
+    if (x >= 0.0 && x <= 20.0 && (double)n == x) return kLogFactorial[n];
+    return lgamma(x + 1.0);
+}
+
+// likelihood part: one 8-lane group per SEGMENT of the rating list (segments longest first, as in the pass kernels: the
+// row is known from the segment descriptor -- no search per rating -- and the four groups of a warp run similar lengths)
+__global__ void __launch_bounds__(256) elbo_like_kernel(const ElboArgs a, const int4* __restrict__ seg_desc, int n_seg) {
     const int lane = threadIdx.x & 31, gl = lane & 7;
-    const int64_t groups = (int64_t)gridDim.x * blockDim.x / 8;
-    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8;
-    const int64_t iters = (nnz + groups - 1) / groups;
+    const unsigned gmask = 0xffu << (lane & ~7);
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8;
     double acc = 0.0;
-    for (int64_t it = 0; it < iters; ++it) {
-        const int64_t t = g0 + it * groups;
-        const bool in = t < nnz;
-        int row = 0;
-        if (in) {   // largest row with row_ptr[row] <= t
-            int lo = 0, hi = a.n_rows;
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.row_ptr[mid] <= t) lo = mid; else hi = mid; }
-            row = lo;
-        }
-        const int c = in ? a.col[t] : 0;
-        float dg = 0.f, de = 0.f;
-        if (in) {
-            const size_t ru = (size_t)(a.row_offset + row) * a.ld, rc = (size_t)c * a.ld;
+    if (gid < n_seg) {
+        const int4 d = __ldg(seg_desc + gid);   // {row, start, end, .}
+        const size_t ru = (size_t)(a.row_offset + d.x) * a.ld;
+        for (int t = d.y; t < d.z; ++t) {
+            const size_t rc = (size_t)__ldg(a.col + t) * a.ld;
+            float dg = 0.f, de = 0.f;
             for (int idx = gl; idx < a.nvec; idx += 8) {
                 const float4 gt = ldg_f4(a.G_theta + ru + idx * 4), gb = ldg_f4(a.G_beta + rc + idx * 4);
                 const float4 et = ldg_f4(a.E_theta + ru + idx * 4), eb = ldg_f4(a.E_beta + rc + idx * 4);
                 dg += gt.x * gb.x + gt.y * gb.y + gt.z * gb.z + gt.w * gb.w;
                 de += et.x * eb.x + et.y * eb.y + et.z * eb.z + et.w * eb.w;
             }
-        }
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            dg += __shfl_xor_sync(0xffffffffu, dg, o);
-            de += __shfl_xor_sync(0xffffffffu, de, o);
-        }
-        if (in && gl == 0) {
-            const double x = (double)a.val[t];
-            acc += x * log(fmax((double)dg, 1e-10)) - lgamma(x + 1.0) - (double)de;
+            for (int o = 4; o > 0; o >>= 1) {
+                dg += __shfl_xor_sync(gmask, dg, o);
+                de += __shfl_xor_sync(gmask, de, o);
+            }
+            if (gl == 0) {
+                const double x = (double)__ldg(a.val + t);
+                acc += x * log(fmax((double)dg, 1e-10)) - log_gamma_x_plus_1(x) - (double)de;
+            }
         }
     }
     __shared__ double s_red[8];
@@ -260,20 +285,28 @@ __global__ void __launch_bounds__(256) elbo_rows_kernel(const float* __restrict_
     double p_fac = 0.0, p_hyp = 0.0, ent = 0.0;
     const int row = row_begin + (int)wid;
     if (row < row_end) {
+        // row constants (hyper_shape is the same for every row of a side; one evaluation per warp is noise)
+        double lg_hs, psi_hs, lg_sp, psi_sp;
+        lgamma_digamma(hyper_shape, lg_hs, psi_hs);
+        lgamma_digamma(shape_prior, lg_sp, psi_sp);
         const double hr = (double)hyper_rate[row];
-        const double Lh = digamma_pos<double>(hyper_shape) - log(hr);   // E log xi
+        const double log_hr = log(hr);
+        const double Lh = psi_hs - log_hr;   // E log xi
         const double Eh = hyper_shape / hr;
+        const double row_const = shape_prior * Lh - lg_sp;
         for (int k = lane; k < K; k += 32) {
             const double s = (double)shp[(size_t)row * ld + k], r = (double)rte[(size_t)row * ld + k];
-            const double ps = digamma_pos<double>(s);
-            const double L = ps - log(r), E = s / r;
-            p_fac += shape_prior * Lh - lgamma(shape_prior) + (shape_prior - 1.0) * L - Eh * E;
-            ent += s - log(r) + lgamma(s) + (1.0 - s) * ps;
+            double lg, ps;
+            lgamma_digamma(s, lg, ps);
+            const double lr = log(r);
+            p_fac += row_const + (shape_prior - 1.0) * (ps - lr) - Eh * (s / r);
+            ent += s - lr + lg + (1.0 - s) * ps;
         }
         if (lane == 0) {
-            p_hyp = hyper_prior_shape * log(hyper_prior_rate) - lgamma(hyper_prior_shape) + (hyper_prior_shape - 1.0) * Lh -
-                    hyper_prior_rate * Eh;
-            ent += hyper_shape - log(hr) + lgamma(hyper_shape) + (1.0 - hyper_shape) * digamma_pos<double>(hyper_shape);
+            double lg_hp, psi_hp;
+            lgamma_digamma(hyper_prior_shape, lg_hp, psi_hp);
+            p_hyp = hyper_prior_shape * log(hyper_prior_rate) - lg_hp + (hyper_prior_shape - 1.0) * Lh - hyper_prior_rate * Eh;
+            ent += hyper_shape - log_hr + lg_hs + (1.0 - hyper_shape) * psi_hs;
         }
     }
     __shared__ double s_red[3][8];
@@ -366,10 +399,8 @@ int pmf_hpf_elbo(const pmf_csr* by_user, int32_t K, int32_t ld, const float* d_E
     e.row_ptr = cv.row_ptr; e.col = cv.col; e.val = cv.val; e.n_rows = cv.n_rows; e.row_offset = cv.row_offset;
     e.K = K; e.ld = ld; e.nvec = ld / 4;
     e.E_theta = d_E_theta; e.E_beta = d_E_beta; e.G_theta = d_G_theta; e.G_beta = d_G_beta; e.out = d_out6;
-    if (cv.nnz > 0) {
-        int64_t blocks = cdiv(cv.nnz, 32);
-        if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
-        elbo_like_kernel<<<(unsigned)blocks, 256, 0, s>>>(e, cv.nnz);
+    if (cv.nnz > 0 && cv.n_seg > 0) {
+        elbo_like_kernel<<<(unsigned)cdiv((int64_t)cv.n_seg * 8, 256), 256, 0, s>>>(e, cv.seg_desc, cv.n_seg);
         PMF_LAUNCH_CHECK();
     }
     if (user_end > user_begin) {

@@ -27,5 +27,5 @@ class GaussianMFCAVI(_WithBias):
     _table_names = ("m_theta", "V_theta", "m_beta", "V_beta")
     _with_bias = False
 
-    def __init__(self, config: GaussianMFCAVIConfig, device=None, seg_len=DEFAULT_SEG_LEN):
-        super().__init__(config, device=device, seg_len=seg_len)
+    def __init__(self, config: GaussianMFCAVIConfig, device=None, seg_len=DEFAULT_SEG_LEN, shard=None):
+        super().__init__(config, device=device, seg_len=seg_len, shard=shard)

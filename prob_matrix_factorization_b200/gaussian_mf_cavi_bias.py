@@ -73,7 +73,19 @@ class GaussEngine:
         self.b_item = torch.zeros(self.M, dtype=torch.float32, device=self.dev) if bias else None
         ws = lambda g: torch.empty(max(_cabi.load().pmf_gauss_workspace_bytes(g.handle, self.K), 16) // 4,
                                    dtype=torch.float32, device=self.dev)
-        self.ws_user, self.ws_item = ws(ratings.by_user), ws(ratings.by_item)
+        self.ws_user = ws(ratings.by_user) if ratings.by_user is not None else None
+        self.ws_item = ws(ratings.by_item)
+        self.world, self.rank = ratings.world, ratings.rank
+        if self.world > 1:
+            # ratings sharded along user ranges (ratings.py): the user passes are local; an item's ratings live on every
+            # rank, so the item passes all-reduce the per-item statistics (NCCL) between accumulation and row update
+            import torch.distributed as dist
+            self.item_sums = f(self.M, self.ldq + self.ld)
+            self.item_resid = torch.zeros(self.M, dtype=torch.float64, device=self.dev)
+            counts = torch.from_numpy(np.diff(ratings.by_item.row_ptr()).astype(np.int32)).to(self.dev)
+            dist.all_reduce(counts)
+            self.item_counts = counts
+        self.launches_per_sweep = 8 if bias else 4
 
     def load(self, m_theta, m_beta):
         """Initial state: given means, V = I, biases 0 (gaussian_mf_cavi_bias.py:52-67)."""
@@ -92,6 +104,8 @@ class GaussEngine:
         c = _cabi.call
         st = _cabi.stream_ptr
         p = _cabi.ptr
+        if self.world > 1:
+            return self._sweep_sharded(sigma2, eta_theta2, eta_beta2, eta_bias2)
         with torch.cuda.device(self.dev):
             c("pmf_gauss_factor_pass", self.r.by_user.handle, self.K, p(self.m_beta), p(self.Q_beta), p(self.b_item),
               p(self.m_theta), p(self.V_theta), p(self.Q_theta), p(self.b_user), sigma2, eta_theta2, p(self.ws_user), st())
@@ -103,6 +117,44 @@ class GaussEngine:
                 c("pmf_gauss_bias_pass", self.r.by_item.handle, self.K, p(self.m_theta), p(self.m_beta), p(self.b_user),
                   p(self.b_item), sigma2, eta_bias2, p(self.ws_item), st())
 
+    def _sweep_sharded(self, sigma2, eta_theta2, eta_beta2, eta_bias2):
+        """The same four passes on one rank's user range: user-side passes are local, item-side passes are split around an
+        NCCL all-reduce of the per-item statistics (row order theta -> beta -> b_u -> b_i as in :132-263)."""
+        import torch.distributed as dist
+        c, st, p = _cabi.call, _cabi.stream_ptr, _cabi.ptr
+        bu, bi = self.r.by_user, self.r.by_item
+        with torch.cuda.device(self.dev):
+            if bu is not None:
+                c("pmf_gauss_factor_pass", bu.handle, self.K, p(self.m_beta), p(self.Q_beta), p(self.b_item),
+                  p(self.m_theta), p(self.V_theta), p(self.Q_theta), p(self.b_user), sigma2, eta_theta2, p(self.ws_user), st())
+            args = (bi.handle, self.K, p(self.m_theta), p(self.Q_theta), p(self.b_user), p(self.m_beta), p(self.V_beta),
+                    p(self.Q_beta), p(self.b_item), sigma2, eta_beta2, p(self.ws_item), p(self.item_sums), p(self.item_counts))
+            c("pmf_gauss_factor_pass_sharded", *args, 1, st())
+            dist.all_reduce(self.item_sums)
+            c("pmf_gauss_factor_pass_sharded", *args, 2, st())
+            if self.bias:
+                if bu is not None:
+                    c("pmf_gauss_bias_pass", bu.handle, self.K, p(self.m_beta), p(self.m_theta), p(self.b_item),
+                      p(self.b_user), sigma2, eta_bias2, p(self.ws_user), st())
+                args = (bi.handle, self.K, p(self.m_theta), p(self.m_beta), p(self.b_user), p(self.b_item), sigma2, eta_bias2,
+                        p(self.ws_item), p(self.item_resid), p(self.item_counts))
+                c("pmf_gauss_bias_pass_sharded", *args, 1, st())
+                dist.all_reduce(self.item_resid)
+                c("pmf_gauss_bias_pass_sharded", *args, 2, st())
+
+    def eval_range(self):
+        return None if self.world == 1 else (self.r.user_lo, self.r.user_hi, self.rank == self.world - 1)
+
+    def sync(self):
+        """Several GPUs, end of fit: the user-side tables live with their owners while the sweeps run -- gather them."""
+        if self.world == 1:
+            return
+        from .parallel import RowExchange
+        xu = RowExchange(self.r.user_bounds)
+        xu.gather(self.m_theta, self.V_theta, self.Q_theta)
+        if self.bias:
+            xu.gather(self.b_user)
+
 
 class GaussianMFCAVI(_DeviceBacked):
     """
@@ -113,8 +165,11 @@ class GaussianMFCAVI(_DeviceBacked):
     _table_names = ("m_theta", "V_theta", "m_beta", "V_beta", "m_user_bias", "m_item_bias")
     _with_bias = True
 
-    def __init__(self, config, device=None, seg_len=DEFAULT_SEG_LEN):
+    def __init__(self, config, device=None, seg_len=DEFAULT_SEG_LEN, shard=None):
+        """``shard=(rank, world)``: one process per GPU, this rank keeps the ratings of one user range (ratings.py); the
+        per-item statistics of the item passes are all-reduced over NCCL, every rank ends with the complete state."""
         self._init_backing()
+        self._shard = shard
         self.config = config
         self.n_users = None
         self.n_items = None
@@ -170,7 +225,8 @@ class GaussianMFCAVI(_DeviceBacked):
             self.n_users, self.n_items = int(np.max(user_ids)) + 1, int(np.max(item_ids)) + 1
         if init is None:
             init = self._initial_state()
-        dr = DeviceRatings(user_ids, item_ids, ratings, self.n_users, self.n_items, self._device, seg_len=self._seg_len)
+        dr = DeviceRatings(user_ids, item_ids, ratings, self.n_users, self.n_items, self._device, seg_len=self._seg_len,
+                           shard=self._shard, item_chunks=1)
         eng = GaussEngine(dr, cfg.n_factors, self._with_bias)
         eng.load(init["m_theta"], init["m_beta"])
         self._engine = eng
@@ -179,11 +235,12 @@ class GaussianMFCAVI(_DeviceBacked):
         self.val_rmse_history_ = []
         ev = None
         if val is not None:
-            ev = EvalSet(val[0], val[1], val[2], self.n_users, self.n_items, eng.dev, drop_invalid=True)
+            ev = EvalSet(val[0], val[1], val[2], self.n_users, self.n_items, eng.dev, drop_invalid=True,
+                         user_range=eng.eval_range())
         eta_bias2 = getattr(cfg, "eta_bias2", 1.0)
         prev_val_rmse = None
         host_iters = range(1, cfg.max_iter + 1)
-        if device_loop_enabled() and not cfg.verbose and cfg.max_iter >= 1:
+        if device_loop_enabled() and not cfg.verbose and cfg.max_iter >= 1 and eng.world == 1:
             host_iters = self._fit_on_device(eng, ev, eta_bias2)
         for it in host_iters:
             if cfg.verbose:
@@ -210,6 +267,7 @@ class GaussianMFCAVI(_DeviceBacked):
                             print("Early stopping: small improvement on validation.")
                         break
                 prev_val_rmse = val_rmse
+        eng.sync()
         self._invalidate()
         return self
 

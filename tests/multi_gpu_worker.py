@@ -116,6 +116,29 @@ def main():
     hist = [O.hpf_elbo(us, is_, xs, O.hpf_sweeps(us, is_, xs, 6, HP, t, 42, Ns, Ms), HP) for t in range(1, 5)]
     report["E"] = rel_max(np.array(me.elbo_history_), np.array(hist))
 
+    # F: Gaussian MF (with and without biases) sharded: item statistics all-reduced over NCCL; early stopping on a sharded
+    #    validation frame takes the same decision on every rank
+    from prob_matrix_factorization_b200 import gaussian_mf_cavi as NB
+    from prob_matrix_factorization_b200.gaussian_mf_cavi_bias import GaussianMFCAVI, GaussianMFCAVIConfig
+    import pandas as pd
+    Ng, Mg, Kg, Tg = 3000, 1800, 10, 6
+    ug, ig, xg = synth.make_ratings(Ng, Mg, 40_000, seed=5)
+    mean = float(xg.mean())
+    xc = xg.astype(np.float64) - mean
+    frame = pd.DataFrame({"u": ug.astype(np.int64), "i": ig.astype(np.int64), "rating": xc})
+    ghp = dict(sigma2=0.5, eta_theta2=0.1, eta_beta2=0.1)
+    for bias in (True, False):
+        if bias:
+            mg = GaussianMFCAVI(GaussianMFCAVIConfig(n_factors=Kg, eta_bias2=0.1, max_iter=Tg, random_state=42, verbose=False, **ghp),
+                                device=dev, shard=(rank, world))
+        else:
+            mg = NB.GaussianMFCAVI(NB.GaussianMFCAVIConfig(n_factors=Kg, max_iter=Tg, random_state=42, verbose=False, **ghp),
+                                   device=dev, shard=(rank, world))
+        mg.fit(frame, global_mean=mean)
+        gref = CO.gauss_sweeps(ug, ig, xc, Ng, Mg, Kg, 0.5, 0.1, 0.1, 0.1, Tg, O.gauss_init(Ng, Mg, Kg, 42), bias=bias)
+        keys = ["m_theta", "V_theta", "m_beta", "V_beta"] + (["m_user_bias", "m_item_bias"] if bias else [])
+        report["F_bias" if bias else "F_nobias"] = max(rel_max(getattr(mg, k), gref[k]) for k in keys)
+
     worst = max(report.values())
     ok = worst < 1e-5 and same and same_stop and ok_state
     print(f"rank {rank}/{world} [{exchange}]: " + " ".join(f"{k}={v:.2e}" for k, v in report.items())
