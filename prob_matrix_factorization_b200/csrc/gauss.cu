@@ -202,111 +202,6 @@ __global__ void __launch_bounds__(256) gauss_solve_kernel(const GaussArgs a) {
     }
 }
 
-// Small K (<= KT <= 12): ONE THREAD per row, everything in registers.  The warp-per-row kernel above leaves 22 of 32 lanes
-// idle at K = 10 and synchronises the warp ~4K times per row (68 + 75 us of a 250 us sweep at C1, ncu); here every row is
-// an independent straight-line float64 computation: P = I/eta2 + S/sigma2 (packed lower triangle), Cholesky P = L L^T in
-// place, then for every unit vector e_c the two triangular solves L y = e_c, L^T v = y give column c of V = P^-1 (full
-// column: V is symmetric, so m = V rhs / sigma2 accumulates as the columns appear); V is written packed, and Q = V + m m^T
-// in a second pass once m is complete.  Loops are unrolled to KT so the arrays live in registers; i, j < K predicates
-// select the live part.
-template <int KT>
-__global__ void __launch_bounds__(128) gauss_solve_small_kernel(const GaussArgs a) {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= a.n_rows) return;
-    if (a.counts ? a.counts[row] == 0 : a.row_ptr[row + 1] == a.row_ptr[row]) return;  // no ratings: keep the state (:134-135)
-    const int K = a.K, W = a.ldq + a.ld;
-    const int s0 = a.row_sums ? row : a.row_seg[row], s1 = a.row_sums ? row + 1 : a.row_seg[row + 1];
-    const float* sums = a.row_sums ? a.row_sums : a.scratch;
-    const double inv_sigma2 = 1.0 / (double)a.sigma2, inv_eta2 = 1.0 / (double)a.eta2;
-    double L[KT * (KT + 1) / 2], rhs[KT], mean[KT];
-#pragma unroll
-    for (int i = 0; i < KT; ++i) {
-        rhs[i] = 0.0; mean[i] = 0.0;
-#pragma unroll
-        for (int j = 0; j <= i; ++j) L[i * (i + 1) / 2 + j] = 0.0;
-    }
-    for (int sg = s0; sg < s1; ++sg) {      // segment sums in segment order
-        const float* src = sums + (size_t)sg * W;
-#pragma unroll
-        for (int i = 0; i < KT; ++i) {
-            if (i < K) {
-                rhs[i] += (double)src[a.ldq + i];
-#pragma unroll
-                for (int j = 0; j <= i; ++j) L[i * (i + 1) / 2 + j] += (double)src[i * (i + 1) / 2 + j];
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < KT; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j) {
-            const int e = i * (i + 1) / 2 + j;
-            L[e] = i < K ? L[e] * inv_sigma2 + (i == j ? inv_eta2 : 0.0) : (i == j ? 1.0 : 0.0);   // identity padding
-        }
-    // Cholesky, column by column; rinv[k] = 1 / L[k][k]
-    double rinv[KT];
-#pragma unroll
-    for (int k = 0; k < KT; ++k) {
-        double d = L[k * (k + 1) / 2 + k];
-#pragma unroll
-        for (int j = 0; j < k; ++j) d -= L[k * (k + 1) / 2 + j] * L[k * (k + 1) / 2 + j];
-        const double rk = rsqrt64(d);
-        rinv[k] = rk;
-        L[k * (k + 1) / 2 + k] = d * rk;
-#pragma unroll
-        for (int i = k + 1; i < KT; ++i) {
-            double t = L[i * (i + 1) / 2 + k];
-#pragma unroll
-            for (int j = 0; j < k; ++j) t -= L[i * (i + 1) / 2 + j] * L[k * (k + 1) / 2 + j];
-            L[i * (i + 1) / 2 + k] = t * rk;
-        }
-    }
-    const size_t R = (size_t)(a.row_offset + row);
-    float* Vrow = a.V_self + R * a.ldq;
-    // columns of V = L^-T L^-1
-#pragma unroll
-    for (int c = 0; c < KT; ++c) {
-        double y[KT];
-#pragma unroll
-        for (int i = 0; i < KT; ++i) {          // L y = e_c  (y_i = 0 for i < c)
-            double t = i == c ? 1.0 : 0.0;
-#pragma unroll
-            for (int j = 0; j < i; ++j)
-                if (j >= c) t -= L[i * (i + 1) / 2 + j] * y[j];
-            y[i] = i >= c ? t * rinv[i] : 0.0;
-        }
-#pragma unroll
-        for (int i = KT - 1; i >= 0; --i) {     // L^T v = y, in place
-            double t = y[i];
-#pragma unroll
-            for (int j = i + 1; j < KT; ++j) t -= L[j * (j + 1) / 2 + i] * y[j];
-            y[i] = t * rinv[i];
-        }
-        if (c < K) {
-#pragma unroll
-            for (int i = 0; i < KT; ++i) {
-                if (i < K) {
-                    mean[i] += y[i] * rhs[c];
-                    if (i >= c) Vrow[i * (i + 1) / 2 + c] = (float)y[i];
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < KT; ++i) {
-        if (i < K) {
-            mean[i] *= inv_sigma2;
-            a.m_self[R * a.ld + i] = (float)mean[i];
-        }
-    }
-    float* Qrow = a.Q_self + R * a.ldq;
-#pragma unroll
-    for (int i = 0; i < KT; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j)
-            if (i < K) Qrow[i * (i + 1) / 2 + j] = (float)((double)Vrow[i * (i + 1) / 2 + j] + mean[i] * mean[j]);   // E[th th^T], :151 / :187
-}
-
 // Bias pass (gaussian_mf_cavi_bias.py:206-263), two kernels so that a row with thousands of ratings is not walked by one
 // warp: (1) one warp per SEGMENT (<= seg_len ratings), 8 lanes per rating compute <m_self[row], m_oth[col]> and the
 // segment's residual sum in float64; (2) one thread per row adds its segments' sums in segment order (deterministic)
@@ -449,13 +344,9 @@ static int gauss_factor_impl(const pmf_csr* csr, int32_t K, const float* d_m_oth
         }
         return PMF_OK;
     }
-    if (c.n_rows > 0 && K <= 12) {
-        const unsigned grid = (unsigned)cdiv(c.n_rows, 128);
-        if (K <= 4) gauss_solve_small_kernel<4><<<grid, 128, 0, s>>>(a);
-        else if (K <= 8) gauss_solve_small_kernel<8><<<grid, 128, 0, s>>>(a);
-        else gauss_solve_small_kernel<12><<<grid, 128, 0, s>>>(a);
-        PMF_LAUNCH_CHECK();
-    } else if (c.n_rows > 0) {
+    // (a one-thread-per-row register Cholesky for K <= 12 was tried and dropped: 252 registers and a ~3000-long dependent
+    // float64 chain per thread made the C1 sweep 0.31 ms instead of 0.21 ms, profiles/README.md)
+    if (c.n_rows > 0) {
         const size_t per_warp = ((size_t)K * (K + 1) + 3 * (size_t)K) * sizeof(double);
         int warps = (int)((size_t)(96 * 1024) / per_warp);       // rows per CTA: as many as fit in 96 KB, at most 8
         warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);

@@ -26,7 +26,7 @@ __device__ __forceinline__ T digamma_pos(T x) {
 //   lgamma(s) = lgamma(x) - log(den),  psi(s) = psi(x) - num/den.
 // Three logarithms and two divisions per call instead of libdevice's lgamma plus a division per shift: the prior /
 // entropy terms of the ELBO evaluate this pair (N + M) K times per sweep and were ~85 % of the ELBO's time.
-__device__ __forceinline__ void lgamma_digamma(double s, double& lg, double& psi) {
+__host__ __device__ __forceinline__ void lgamma_digamma(double s, double& lg, double& psi) {
     double x = s, num = 0.0, den = 1.0;
 #pragma unroll 1
     while (x < 8.0) { num = num * x + den; den *= x; x += 1.0; }
@@ -289,20 +289,21 @@ __global__ void __launch_bounds__(256) elbo_like_kernel(const ElboArgs a, const 
 
 // prior + entropy terms of one side: rows [row_begin, row_end).  out[slot_p] += E log p(factor | hyper),
 // out[slot_h] += E log p(hyper), out[5] += entropies.
+struct ElboRowConsts {   // lgamma / digamma of the three shape constants of a side, evaluated once on the host
+    double lg_hs, psi_hs, lg_sp, lg_hp;
+};
+
 __global__ void __launch_bounds__(256) elbo_rows_kernel(const float* __restrict__ shp, const float* __restrict__ rte,
                                                         const float* __restrict__ hyper_rate, int row_begin, int row_end,
                                                         int K, int ld, double shape_prior, double hyper_shape,
                                                         double hyper_prior_shape, double hyper_prior_rate, double* out,
-                                                        int slot_p, int slot_h) {
+                                                        int slot_p, int slot_h, const ElboRowConsts cst) {
     const int lane = threadIdx.x & 31;
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     double p_fac = 0.0, p_hyp = 0.0, ent = 0.0;
     const int row = row_begin + (int)wid;
     if (row < row_end) {
-        // row constants (hyper_shape is the same for every row of a side; one evaluation per warp is noise)
-        double lg_hs, psi_hs, lg_sp, psi_sp;
-        lgamma_digamma(hyper_shape, lg_hs, psi_hs);
-        lgamma_digamma(shape_prior, lg_sp, psi_sp);
+        const double lg_hs = cst.lg_hs, psi_hs = cst.psi_hs, lg_sp = cst.lg_sp;
         const double hr = (double)hyper_rate[row];
         const double log_hr = log(hr);
         const double Lh = psi_hs - log_hr;   // E log xi
@@ -318,8 +319,7 @@ __global__ void __launch_bounds__(256) elbo_rows_kernel(const float* __restrict_
             ent += (double)(s - lr + lg + (1.f - s) * ps);
         }
         if (lane == 0) {
-            double lg_hp, psi_hp;
-            lgamma_digamma(hyper_prior_shape, lg_hp, psi_hp);
+            const double lg_hp = cst.lg_hp;
             p_hyp = hyper_prior_shape * log(hyper_prior_rate) - lg_hp + (hyper_prior_shape - 1.0) * Lh - hyper_prior_rate * Eh;
             ent += hyper_shape - log_hr + lg_hs + (1.0 - hyper_shape) * psi_hs;
         }
@@ -418,16 +418,26 @@ int pmf_hpf_elbo(const pmf_csr* by_user, int32_t K, int32_t ld, const float* d_E
         elbo_like_kernel<<<(unsigned)cdiv((int64_t)cv.n_seg * 8, 256), 256, 0, s>>>(e, cv.seg_desc, cv.n_seg);
         PMF_LAUNCH_CHECK();
     }
+    auto consts = [](double shape_prior, double hyper_shape, double hyper_prior_shape) {
+        ElboRowConsts k;
+        double unused;
+        lgamma_digamma(hyper_shape, k.lg_hs, k.psi_hs);
+        lgamma_digamma(shape_prior, k.lg_sp, unused);
+        lgamma_digamma(hyper_prior_shape, k.lg_hp, unused);
+        return k;
+    };
     if (user_end > user_begin) {
+        const double hs = (double)a_prime + K * (double)a;
         elbo_rows_kernel<<<(unsigned)cdiv((int64_t)(user_end - user_begin) * 32, 256), 256, 0, s>>>(
-            d_shp_theta, d_rte_theta, d_rate_xi, user_begin, user_end, K, ld, (double)a, (double)a_prime + K * (double)a,
-            (double)a_prime, (double)b_prime, d_out6, 1, 3);
+            d_shp_theta, d_rte_theta, d_rate_xi, user_begin, user_end, K, ld, (double)a, hs,
+            (double)a_prime, (double)b_prime, d_out6, 1, 3, consts((double)a, hs, (double)a_prime));
         PMF_LAUNCH_CHECK();
     }
     if (item_end > item_begin) {
+        const double hs = (double)c_prime + K * (double)c;
         elbo_rows_kernel<<<(unsigned)cdiv((int64_t)(item_end - item_begin) * 32, 256), 256, 0, s>>>(
-            d_shp_beta, d_rte_beta, d_rate_eta, item_begin, item_end, K, ld, (double)c, (double)c_prime + K * (double)c,
-            (double)c_prime, (double)d_prime, d_out6, 2, 4);
+            d_shp_beta, d_rte_beta, d_rate_eta, item_begin, item_end, K, ld, (double)c, hs,
+            (double)c_prime, (double)d_prime, d_out6, 2, 4, consts((double)c, hs, (double)c_prime));
         PMF_LAUNCH_CHECK();
     }
     return PMF_OK;
