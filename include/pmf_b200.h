@@ -99,6 +99,15 @@ int pmf_coo_partition(const int32_t* d_u, const int32_t* d_i, const float* d_x, 
                       const int32_t* h_bounds, int32_t n_buckets, int32_t* d_u_out, int32_t* d_i_out, float* d_x_out,
                       int64_t* h_offsets, void* stream);
 
+/* ---- a2: initial state (host) ---------------------------------------------------------------------------------------
+ * h_out[k] = offset + scale * E_k, k < n, where E_k is the stream np.random.Generator(PCG64).gamma(1.0, 1.0) produces from
+ * the given bit-generator state -- the reference's initial draws `a + rng.gamma(1.0, 0.1, size=(R, K))`
+ * (poisson_mf_cavi.py:62-63, hpf_cavi.py:71-80), bit for bit, computed by `threads` host threads (<= 0: all cores).
+ * state / inc: the two 128-bit PCG64 words as {high, low} uint64 pairs (`rng.bit_generator.state["state"]`);
+ * new_state_hi_lo receives the state after the n variates (what NumPy's generator would hold).  Host memory only. */
+int pmf_numpy_exponential_fill(const uint64_t* state_hi_lo, const uint64_t* inc_hi_lo, double scale, double offset,
+                               int64_t n, double* h_out, int32_t threads, uint64_t* new_state_hi_lo);
+
 /* ---- a3/a4: Gamma-Poisson row pass (Poisson MF and HPF-CAVI) ------------------------
  * Replaces the per-row loops poisson_mf_cavi.py:135-164 / :173-194 (+ E=a/b :167,:197) and
  * hpf_cavi.py:126-151 / :162-185 (+ :153, :158-159, :187, :192-193).  For every row r of `csr`

@@ -15,6 +15,7 @@ import numpy as np
 from . import _cabi
 from ._engine import (DeviceLoop, EvalSet, GammaEngine, Trace, device_loop_enabled, eval_stats, eval_stats_launch,
                       normalise_ids, predict, row_stride, table_to_host)
+from .host_draws import gamma_shape1
 from .poisson_mf_cavi import _DeviceBacked
 from .ratings import DEFAULT_SEG_LEN, DeviceRatings, to_device
 
@@ -85,10 +86,11 @@ class HPF_CAVI(_DeviceBacked):
         cfg = self.config
         rng = np.random.default_rng(cfg.random_state)
         K, N, M = cfg.n_factors, self.n_users, self.n_items
-        a_t = cfg.a + rng.gamma(1.0, 0.1, size=(N, K))
-        b_t = cfg.b_prime + rng.gamma(1.0, 0.1, size=(N, K))
-        a_b = cfg.c + rng.gamma(1.0, 0.1, size=(M, K))
-        b_b = cfg.d_prime + rng.gamma(1.0, 0.1, size=(M, K))
+        # cfg.a + rng.gamma(1.0, 0.1, size=(N, K)) etc., bit for bit (host_draws: NumPy's stream replayed by all host cores)
+        a_t = gamma_shape1(rng, 0.1, (N, K), cfg.a)
+        b_t = gamma_shape1(rng, 0.1, (N, K), cfg.b_prime)
+        a_b = gamma_shape1(rng, 0.1, (M, K), cfg.c)
+        b_b = gamma_shape1(rng, 0.1, (M, K), cfg.d_prime)
         a_xi = cfg.a_prime + K * cfg.a
         a_eta = cfg.c_prime + K * cfg.c
         b_xi = cfg.b_prime * np.ones(N)

@@ -23,6 +23,7 @@ import torch
 from . import _cabi
 from ._engine import (DeviceLoop, EvalSet, GammaEngine, device_loop_enabled, eval_stats, eval_stats_launch, normalise_ids,
                       predict, row_stride, table_to_host)
+from .host_draws import gamma_shape1
 from .ratings import DEFAULT_SEG_LEN, DeviceRatings, to_device
 
 
@@ -108,8 +109,9 @@ class PoissonMFCAVI(_DeviceBacked):
         """Host draws in the reference's order (poisson_mf_cavi.py:50-71)."""
         rng = np.random.default_rng(self.config.random_state)
         K = self.config.n_factors
-        a_theta = self.config.a0 + rng.gamma(1.0, 0.1, size=(self.n_users, K))
-        a_beta = self.config.a0 + rng.gamma(1.0, 0.1, size=(self.n_items, K))
+        # a0 + rng.gamma(1.0, 0.1, size=...), bit for bit (host_draws: NumPy's stream replayed by all host cores)
+        a_theta = gamma_shape1(rng, 0.1, (self.n_users, K), self.config.a0)
+        a_beta = gamma_shape1(rng, 0.1, (self.n_items, K), self.config.a0)
         return {"a_theta": a_theta, "a_beta": a_beta,
                 "E_theta": a_theta / self.config.b0, "E_beta": a_beta / self.config.b0}
 
