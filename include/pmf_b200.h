@@ -108,6 +108,12 @@ int pmf_coo_partition(const int32_t* d_u, const int32_t* d_i, const float* d_x, 
 int pmf_numpy_exponential_fill(const uint64_t* state_hi_lo, const uint64_t* inc_hi_lo, double scale, double offset,
                                int64_t n, double* h_out, int32_t threads, uint64_t* new_state_hi_lo);
 
+/* Multi-threaded host conversions of the reference's input dtypes (DataFrame columns are int64 / float64,
+ * load_data.py:93-105; NumPy state is float64): int64 -> int32 with the range of the input (callers reject ids outside
+ * [0, 2^31-2]) and float64 -> float32 (round to nearest, what NumPy's astype does).  Host memory only. */
+int pmf_host_i64_to_i32(const int64_t* h_in, int64_t n, int32_t* h_out, int64_t* h_min, int64_t* h_max, int32_t threads);
+int pmf_host_f64_to_f32(const double* h_in, int64_t n, float* h_out, int32_t threads);
+
 /* ---- a3/a4: Gamma-Poisson row pass (Poisson MF and HPF-CAVI) ------------------------
  * Replaces the per-row loops poisson_mf_cavi.py:135-164 / :173-194 (+ E=a/b :167,:197) and
  * hpf_cavi.py:126-151 / :162-185 (+ :153, :158-159, :187, :192-193).  For every row r of `csr`

@@ -59,6 +59,8 @@ _PROTOTYPES = {
     "pmf_coo_partition": (C.c_int, [VP, VP, VP, C.c_int64, C.c_int32, c_i32p, C.c_int32, VP, VP, VP,
                                     C.POINTER(C.c_int64), VP]),
     "pmf_trim": (C.c_int, []),
+    "pmf_host_i64_to_i32": (C.c_int, [VP, C.c_int64, VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]),
+    "pmf_host_f64_to_f32": (C.c_int, [VP, C.c_int64, VP, C.c_int32]),
     "pmf_numpy_exponential_fill": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_double, C.c_double, C.c_int64,
                                              VP, C.c_int32, C.POINTER(C.c_uint64)]),
     "pmf_memcpy_async": (C.c_int, [VP, VP, C.c_int64, VP]),

@@ -50,6 +50,9 @@ def pad_table(host, ld, device):
     """
     host = np.asarray(host)
     R, K = host.shape
+    if host.dtype == np.float64 and host.size >= (1 << 20):
+        from .host_draws import to_float32          # halve the H2D bytes; the cast runs on all host cores
+        host = to_float32(np.ascontiguousarray(host))
     src = torch.from_numpy(np.ascontiguousarray(host))
     if src.dtype == torch.float32 and K == ld:
         return src.to(device, non_blocking=True)

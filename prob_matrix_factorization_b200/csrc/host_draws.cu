@@ -415,3 +415,44 @@ extern "C" int pmf_numpy_exponential_fill(const uint64_t* state_hi_lo, const uin
     new_state_hi_lo[1] = (uint64_t)fin.state;
     return PMF_OK;
 }
+
+// ---- multi-threaded host conversions of the reference's input dtypes -----------------------------------------------
+// A DataFrame hands fit() int64 ids and float64 ratings (load_data.py:93-105), NumPy state is float64; the engine wants
+// int32 / float32.  Single-threaded NumPy astype + min + max over the 100 M-rating config cost ~0.6 s of fit(DataFrame).
+namespace {
+template <typename Fn>
+void parallel_ranges(int64_t n, int threads, Fn&& fn) {
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    threads = (int)std::min<int64_t>(threads, std::max<int64_t>(1, n / (1 << 16)));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&, t]() { fn(t, n * t / threads, n * (t + 1) / threads); });
+    for (auto& th : pool) th.join();
+}
+}  // namespace
+
+extern "C" int pmf_host_i64_to_i32(const int64_t* h_in, int64_t n, int32_t* h_out, int64_t* h_min, int64_t* h_max, int32_t threads) {
+    PMF_REQUIRE(n >= 0 && (n == 0 || (h_in && h_out)) && h_min && h_max, "bad argument");
+    std::vector<int64_t> lo(256, INT64_MAX), hi(256, INT64_MIN);
+    if (threads > 256) threads = 256;
+    parallel_ranges(n, threads, [&](int t, int64_t a, int64_t b) {
+        int64_t mn = INT64_MAX, mx = INT64_MIN;
+        for (int64_t k = a; k < b; ++k) {
+            const int64_t v = h_in[k];
+            mn = v < mn ? v : mn; mx = v > mx ? v : mx;
+            h_out[k] = (int32_t)v;
+        }
+        lo[t] = mn; hi[t] = mx;
+    });
+    *h_min = *std::min_element(lo.begin(), lo.end());
+    *h_max = *std::max_element(hi.begin(), hi.end());
+    return PMF_OK;
+}
+
+extern "C" int pmf_host_f64_to_f32(const double* h_in, int64_t n, float* h_out, int32_t threads) {
+    PMF_REQUIRE(n >= 0 && (n == 0 || (h_in && h_out)), "bad argument");
+    parallel_ranges(n, threads > 256 ? 256 : threads, [&](int, int64_t a, int64_t b) {
+        for (int64_t k = a; k < b; ++k) h_out[k] = (float)h_in[k];
+    });
+    return PMF_OK;
+}

@@ -46,3 +46,29 @@ def gamma_shape1(rng, scale, size, offset=0.0, threads=None):
     st["state"]["state"] = (int(s_out[0]) << 64) | int(s_out[1])
     bg.state = st
     return out
+
+
+MIN_PARALLEL_CAST = 1 << 20
+
+
+def ids_to_int32(a, name="id"):
+    """Contiguous int64 host ids -> int32 (with the range check of ``ratings.as_id_array``), by all host cores."""
+    a = np.ascontiguousarray(a)
+    if a.dtype != np.int64 or a.size < MIN_PARALLEL_CAST:
+        return None
+    out = np.empty(a.shape, dtype=np.int32)
+    lo, hi = C.c_int64(0), C.c_int64(0)
+    _cabi.call("pmf_host_i64_to_i32", a.ctypes.data, a.size, out.ctypes.data, C.byref(lo), C.byref(hi), host_threads())
+    if lo.value < 0 or hi.value > np.iinfo(np.int32).max - 1:
+        raise ValueError(f"{name} ids must lie in [0, 2^31-2]")
+    return out
+
+
+def to_float32(a):
+    """float64 host array -> float32 (NumPy's rounding), by all host cores for large arrays."""
+    a = np.asarray(a)
+    if a.dtype != np.float64 or a.size < MIN_PARALLEL_CAST or not a.flags.c_contiguous:
+        return np.asarray(a, dtype=np.float32)
+    out = np.empty(a.shape, dtype=np.float32)
+    _cabi.call("pmf_host_f64_to_f32", a.ctypes.data, a.size, out.ctypes.data, host_threads())
+    return out

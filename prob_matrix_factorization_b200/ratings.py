@@ -47,6 +47,11 @@ def auto_seg_len(nnz):
 def as_id_array(a, name):
     """Host ids -> contiguous int32 NumPy (reference: ``to_numpy(dtype=int)``)."""
     a = np.asarray(a)
+    if a.dtype == np.int64:
+        from .host_draws import ids_to_int32        # large arrays: cast + range check by all host cores
+        fast = ids_to_int32(a, name)
+        if fast is not None:
+            return fast
     if a.dtype != np.int32:
         if a.size and (a.min() < 0 or a.max() > np.iinfo(np.int32).max - 1):
             raise ValueError(f"{name} ids must lie in [0, 2^31-2]")
@@ -203,7 +208,11 @@ class DeviceRatings:
         self.rank, self.world = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
         u_h = u if isinstance(u, torch.Tensor) else as_id_array(u, "user")
         i_h = i if isinstance(i, torch.Tensor) else as_id_array(i, "item")
-        x_h = x if isinstance(x, torch.Tensor) else np.asarray(x, dtype=np.float32)
+        if isinstance(x, torch.Tensor):
+            x_h = x
+        else:
+            from .host_draws import to_float32
+            x_h = to_float32(x)
         if not (len(u_h) == len(i_h) == len(x_h)):
             raise ValueError("u, i, rating must have equal length")
         if self.world > 1:

@@ -40,3 +40,22 @@ def test_small_sizes_and_buffered_generators_fall_back_to_numpy():
     n = host_draws.MIN_PARALLEL + 17
     assert np.array_equal(host_draws.gamma_shape1(rng, 0.1, n), ref.gamma(1.0, 0.1, size=n))
     assert rng.bit_generator.state == ref.bit_generator.state
+
+
+def test_parallel_host_casts_equal_numpy():
+    rng = np.random.default_rng(0)
+    ids = rng.integers(0, 2_000_000, size=host_draws.MIN_PARALLEL_CAST + 12345, dtype=np.int64)
+    got = host_draws.ids_to_int32(ids)
+    assert got.dtype == np.int32 and np.array_equal(got, ids.astype(np.int32))
+    assert host_draws.ids_to_int32(ids[:100]) is None and host_draws.ids_to_int32(ids.astype(np.int32)) is None
+    bad = ids.copy(); bad[777] = -1
+    with pytest.raises(ValueError):
+        host_draws.ids_to_int32(bad)
+    bad[777] = 2 ** 31 - 1
+    with pytest.raises(ValueError):
+        host_draws.ids_to_int32(bad)
+    x = rng.standard_normal((host_draws.MIN_PARALLEL_CAST // 8 + 3, 8)) * 1e3
+    f = host_draws.to_float32(x)
+    assert f.dtype == np.float32 and f.shape == x.shape and np.array_equal(f, x.astype(np.float32))
+    from prob_matrix_factorization_b200.ratings import as_id_array
+    assert np.array_equal(as_id_array(ids, "user"), ids.astype(np.int32))
