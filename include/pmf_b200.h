@@ -113,6 +113,8 @@ int pmf_numpy_exponential_fill(const uint64_t* state_hi_lo, const uint64_t* inc_
  * [0, 2^31-2]) and float64 -> float32 (round to nearest, what NumPy's astype does).  Host memory only. */
 int pmf_host_i64_to_i32(const int64_t* h_in, int64_t n, int32_t* h_out, int64_t* h_min, int64_t* h_max, int32_t threads);
 int pmf_host_f64_to_f32(const double* h_in, int64_t n, float* h_out, int32_t threads);
+/* h_out = h_a / h_b element-wise (h_b == NULL: / b_scalar): the initial expectations E = shape / rate (hpf_cavi.py:91-95). */
+int pmf_host_divide_f64(const double* h_a, const double* h_b, double b_scalar, int64_t n, double* h_out, int32_t threads);
 
 /* ---- a3/a4: Gamma-Poisson row pass (Poisson MF and HPF-CAVI) ------------------------
  * Replaces the per-row loops poisson_mf_cavi.py:135-164 / :173-194 (+ E=a/b :167,:197) and

@@ -61,6 +61,7 @@ _PROTOTYPES = {
     "pmf_trim": (C.c_int, []),
     "pmf_host_i64_to_i32": (C.c_int, [VP, C.c_int64, VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]),
     "pmf_host_f64_to_f32": (C.c_int, [VP, C.c_int64, VP, C.c_int32]),
+    "pmf_host_divide_f64": (C.c_int, [VP, VP, C.c_double, C.c_int64, VP, C.c_int32]),
     "pmf_numpy_exponential_fill": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_double, C.c_double, C.c_int64,
                                              VP, C.c_int32, C.POINTER(C.c_uint64)]),
     "pmf_memcpy_async": (C.c_int, [VP, VP, C.c_int64, VP]),

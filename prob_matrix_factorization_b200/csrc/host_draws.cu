@@ -456,3 +456,13 @@ extern "C" int pmf_host_f64_to_f32(const double* h_in, int64_t n, float* h_out, 
     });
     return PMF_OK;
 }
+
+// out = a / b (b_scalar when h_b == NULL): IEEE float64 division, i.e. exactly NumPy's a / b, by all host cores
+extern "C" int pmf_host_divide_f64(const double* h_a, const double* h_b, double b_scalar, int64_t n, double* h_out, int32_t threads) {
+    PMF_REQUIRE(n >= 0 && (n == 0 || (h_a && h_out)), "bad argument");
+    parallel_ranges(n, threads > 256 ? 256 : threads, [&](int, int64_t lo, int64_t hi) {
+        if (h_b) for (int64_t k = lo; k < hi; ++k) h_out[k] = h_a[k] / h_b[k];
+        else for (int64_t k = lo; k < hi; ++k) h_out[k] = h_a[k] / b_scalar;
+    });
+    return PMF_OK;
+}

@@ -72,3 +72,17 @@ def to_float32(a):
     out = np.empty(a.shape, dtype=np.float32)
     _cabi.call("pmf_host_f64_to_f32", a.ctypes.data, a.size, out.ctypes.data, host_threads())
     return out
+
+
+def divide(a, b):
+    """``a / b`` for a float64 array ``a`` and an equally shaped float64 array or a scalar ``b`` (IEEE division, bit-identical
+    to NumPy), by all host cores for large arrays."""
+    a = np.asarray(a)
+    scalar = np.isscalar(b)
+    if (a.dtype != np.float64 or a.size < MIN_PARALLEL_CAST or not a.flags.c_contiguous
+            or (not scalar and (b.dtype != np.float64 or b.shape != a.shape or not b.flags.c_contiguous))):
+        return a / b
+    out = np.empty(a.shape, dtype=np.float64)
+    _cabi.call("pmf_host_divide_f64", a.ctypes.data, None if scalar else b.ctypes.data, float(b) if scalar else 0.0, a.size,
+               out.ctypes.data, host_threads())
+    return out

@@ -15,7 +15,7 @@ import numpy as np
 from . import _cabi
 from ._engine import (DeviceLoop, EvalSet, GammaEngine, Trace, device_loop_enabled, eval_stats, eval_stats_launch,
                       normalise_ids, predict, row_stride, table_to_host)
-from .host_draws import gamma_shape1
+from .host_draws import divide, gamma_shape1
 from .poisson_mf_cavi import _DeviceBacked
 from .ratings import DEFAULT_SEG_LEN, DeviceRatings, to_device
 
@@ -97,7 +97,7 @@ class HPF_CAVI(_DeviceBacked):
         b_eta = cfg.d_prime * np.ones(M)
         return {"gamma_a_theta": a_t, "gamma_b_theta": b_t, "gamma_a_beta": a_b, "gamma_b_beta": b_b,
                 "gamma_a_xi": a_xi, "gamma_a_eta": a_eta, "gamma_b_xi": b_xi, "gamma_b_eta": b_eta,
-                "E_theta": a_t / b_t, "E_beta": a_b / b_b, "E_xi": a_xi / b_xi, "E_eta": a_eta / b_eta}
+                "E_theta": divide(a_t, b_t), "E_beta": divide(a_b, b_b), "E_xi": a_xi / b_xi, "E_eta": a_eta / b_eta}
 
     def _materialise(self, name):
         eng = self._engine

@@ -23,7 +23,7 @@ import torch
 from . import _cabi
 from ._engine import (DeviceLoop, EvalSet, GammaEngine, device_loop_enabled, eval_stats, eval_stats_launch, normalise_ids,
                       predict, row_stride, table_to_host)
-from .host_draws import gamma_shape1
+from .host_draws import divide, gamma_shape1
 from .ratings import DEFAULT_SEG_LEN, DeviceRatings, to_device
 
 
@@ -113,7 +113,7 @@ class PoissonMFCAVI(_DeviceBacked):
         a_theta = gamma_shape1(rng, 0.1, (self.n_users, K), self.config.a0)
         a_beta = gamma_shape1(rng, 0.1, (self.n_items, K), self.config.a0)
         return {"a_theta": a_theta, "a_beta": a_beta,
-                "E_theta": a_theta / self.config.b0, "E_beta": a_beta / self.config.b0}
+                "E_theta": divide(a_theta, float(self.config.b0)), "E_beta": divide(a_beta, float(self.config.b0))}
 
     def _materialise(self, name):
         eng = self._engine

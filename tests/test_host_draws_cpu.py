@@ -59,3 +59,12 @@ def test_parallel_host_casts_equal_numpy():
     assert f.dtype == np.float32 and f.shape == x.shape and np.array_equal(f, x.astype(np.float32))
     from prob_matrix_factorization_b200.ratings import as_id_array
     assert np.array_equal(as_id_array(ids, "user"), ids.astype(np.int32))
+
+
+def test_parallel_divide_equals_numpy():
+    rng = np.random.default_rng(1)
+    a = rng.gamma(1.0, 0.1, size=(host_draws.MIN_PARALLEL_CAST // 4 + 5, 4)) + 0.3
+    b = rng.gamma(1.0, 0.1, size=a.shape) + 5.0
+    assert np.array_equal(host_draws.divide(a, b), a / b)
+    assert np.array_equal(host_draws.divide(a, 0.5), a / 0.5)
+    assert np.array_equal(host_draws.divide(a[:10], b[:10]), a[:10] / b[:10])
