@@ -142,7 +142,7 @@ class HPF_CAVI(_DeviceBacked):
         hyper = {"user_shape": float(init["gamma_a_xi"]), "user_rate_prior": float(cfg.b_prime),
                  "item_shape": float(init["gamma_a_eta"]), "item_rate_prior": float(cfg.d_prime)}
         eng = GammaEngine(dr, cfg.n_factors, cfg.a, cfg.c, None, None, hyper=hyper, **self._engine_kw)
-        tr.mark("engine tables (+ symmetric memory / IPC)")
+        tr.mark("engine tables (+ symmetric memory)")
         eng.load_means(init["E_theta"], init["E_beta"], init["E_xi"], init["E_eta"])
         tr.mark("initial factors H2D")
         if self._allocation == "digamma" or self._track_elbo:
@@ -198,7 +198,7 @@ class HPF_CAVI(_DeviceBacked):
         eng.sync_params()
         tr.mark("gather shape/rate tables")
         if self._auto_close:
-            eng.close()                   # peer-mapped tables (multi-GPU) become ordinary device tensors
+            eng.close()                   # symmetric-memory tables (multi-GPU) become ordinary device tensors
         if self.n_iter_ > 0:
             self._init = None
         self._invalidate()

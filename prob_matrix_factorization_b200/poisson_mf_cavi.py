@@ -202,7 +202,7 @@ class PoissonMFCAVI(_DeviceBacked):
                 prev_val_rmse = val_rmse
         eng.sync_params()
         if self._auto_close:
-            eng.close()                   # peer-mapped tables (multi-GPU) become ordinary device tensors
+            eng.close()                   # symmetric-memory tables (multi-GPU) become ordinary device tensors
         self._invalidate()
         if self.n_iter_ == 0:
             self._host.update({"a_theta": init["a_theta"], "a_beta": init["a_beta"]})

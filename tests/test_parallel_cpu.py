@@ -1,5 +1,10 @@
-"""N>1 host logic on CPU: world_size-2 gloo.  Row-aligned nnz-balanced shard plan + the row exchange
-that replaces the statistics all-reduce; the per-shard maths is stood in for by the oracle (tests only)."""
+"""N>1 host logic on CPU: world_size-2 gloo; the per-shard maths is stood in for by the oracle (tests only).
+
+* the round-2 scheme end to end (test_user_range_sharding_gloo): every rank takes 1/world of the list, a histogram all-reduce
+  gives nnz-balanced user ranges, a stable split + all-to-all routes each rating to its user's owner in original order, the
+  user pass is local, the item pass's per-rank partial row sums are all-reduced ("sufficient statistics combine") -- equal
+  to the single-rank result;
+* RowExchange (the end-of-fit gather of owned rows) on row-aligned shards, and the bounds / chunk / ownership helpers."""
 import os
 import socket
 
@@ -88,6 +93,80 @@ def test_sharded_sweeps_equal_single_rank_gloo():
     for rank, err, nbytes in res:
         assert err < 1e-12, (rank, err)      # row-aligned shards: bit-identical maths, no cross-rank sums
         assert nbytes > 0
+
+
+def _worker_user_sharded(rank, world, port, q):
+    from prob_matrix_factorization_b200.parallel import balanced_bounds_from_counts
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        N, M, nnz, K, T = 500, 350, 9000, 4, 3
+        u, i, x = synth.make_ratings(N, M, nnz, seed=8)
+        u = u.astype(np.int64); i = i.astype(np.int64); x = x.astype(np.float64) + 1.0
+        cfg = dict(a=0.3, a_prime=5.0, b_prime=5.0, c=0.3, c_prime=5.0, d_prime=5.0)
+        # --- routing, as ratings.DeviceRatings._route_to_owner does it on the device ---
+        per = (nnz + world - 1) // world
+        lo, hi = rank * per, min((rank + 1) * per, nnz)
+        uc, ic, xc = u[lo:hi], i[lo:hi], x[lo:hi]                       # this rank's piece of the list
+        counts = torch.from_numpy(np.bincount(uc, minlength=N))
+        dist.all_reduce(counts)
+        bounds = balanced_bounds_from_counts(counts.numpy(), world)
+        owner = np.searchsorted(bounds[1:], uc, side="right")
+        order = np.argsort(owner, kind="stable")                          # = pmf_coo_partition
+        send = torch.from_numpy(np.bincount(owner, minlength=world))
+        recv = torch.zeros(world, dtype=torch.int64)
+        dist.all_to_all_single(recv, send)
+        got = []
+        for src in (uc[order], ic[order], xc[order]):
+            dst = torch.zeros(int(recv.sum()), dtype=torch.from_numpy(src).dtype)
+            dist.all_to_all_single(dst, torch.from_numpy(np.ascontiguousarray(src)), recv.tolist(), send.tolist())
+            got.append(dst.numpy())
+        ul, il, xl = got
+        mine = (u >= bounds[rank]) & (u < bounds[rank + 1])
+        routed_ok = np.array_equal(ul, u[mine]) and np.array_equal(il, i[mine]) and np.array_equal(xl, x[mine])   # original order kept
+        # --- sweeps: local user pass; item pass = per-rank partial sums, all-reduced, then the row update ---
+        st = O.hpf_init(N, M, K, cfg, 42)
+        E_t, E_b, E_x, E_e = st["E_theta"].copy(), st["E_beta"].copy(), st["E_xi"].copy(), st["E_eta"].copy()
+        ulo, uhi = int(bounds[rank]), int(bounds[rank + 1])
+        rp_u, pm_u = O.group_observations(ul - ulo, uhi - ulo)
+        rp_i, pm_i = O.group_observations(il, M)
+        for _ in range(T):
+            shp, rte = O.gamma_row_pass(rp_u, pm_u, il, xl, E_t[ulo:uhi], E_b, cfg["a"], E_x[ulo:uhi])
+            E_t[ulo:uhi] = shp / rte
+            E_x[ulo:uhi] = st["gamma_a_xi"] / (cfg["b_prime"] + E_t[ulo:uhi].sum(1))
+            # partial sums over THIS rank's ratings: zero priors give E_beta * sum (x/rate) E_theta  and  sum E_theta
+            part_a, part_b = O.gamma_row_pass(rp_i, pm_i, ul, xl, E_b, E_t, 0.0, np.zeros(M))
+            stats = torch.from_numpy(np.concatenate([part_a, part_b], axis=1))
+            dist.all_reduce(stats)                                         # the sufficient-statistics combine
+            tot = stats.numpy()
+            shp_b, rte_b = cfg["c"] + tot[:, :K], E_e[:, None] + tot[:, K:]
+            E_b = shp_b / rte_b
+            E_e = st["gamma_a_eta"] / (cfg["d_prime"] + E_b.sum(1))
+        # owned user rows of every rank together = the full table
+        full_t = torch.zeros(N, K, dtype=torch.float64); full_t[ulo:uhi] = torch.from_numpy(E_t[ulo:uhi])
+        dist.all_reduce(full_t)
+        ref = O.hpf_sweeps(u, i, x, K, cfg, T, 42, N, M)
+        err = max(np.abs(full_t.numpy() - ref["E_theta"]).max(), np.abs(E_b - ref["E_beta"]).max(), np.abs(E_e - ref["E_eta"]).max())
+        q.put((rank, bool(routed_ok), float(err)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_user_range_sharding_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_user_sharded, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, routed_ok, err in res:
+        assert routed_ok, rank                  # every rank holds exactly its users' ratings, in original order
+        assert err < 1e-12, (rank, err)          # cross-rank sums change only the float64 summation order
 
 
 def test_item_chunks_and_owned_ranges_partition_the_items():
