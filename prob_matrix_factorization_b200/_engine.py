@@ -293,7 +293,9 @@ class GammaEngine:
         self.keep_params = keep_params
         f = lambda rows, cols=self.ld: torch.zeros((rows, cols), dtype=torch.float32, device=self.dev)
         if exchange is None:
-            exchange = os.environ.get("PMF_EXCHANGE", "mc")
+            # measured (profiles/README.md): 2 GPUs -- staging by the copy engines 2.94 ms vs in-switch 3.08 ms per sweep;
+            # 8 GPUs -- in-switch 1.16 ms vs staged 1.90 ms (seven small peer copies per rank reach only ~200 GB/s)
+            exchange = os.environ.get("PMF_EXCHANGE") or ("ce" if ratings.world == 2 else "mc")
         if exchange not in ("mc", "ce", "nccl"):
             raise ValueError("exchange must be 'mc', 'ce' or 'nccl'")
         self.exchange = exchange if self.world > 1 else "none"
