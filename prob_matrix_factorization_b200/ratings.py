@@ -228,8 +228,8 @@ class DeviceRatings:
         self.user_lo, self.user_hi = int(self.user_bounds[self.rank]), int(self.user_bounds[self.rank + 1])
         # several GPUs: the item rows can be processed in chunks so that the cross-rank combine of one chunk overlaps the
         # pass over the next (GammaEngine.item_pass); the number is fixed here because it sets the size of a launch.
-        # Default 1: measured on 8 B200 (profiles/README.md) chunking never paid -- the pass kernels fill every SM, so the
-        # combine of a chunk only gets SMs when the next chunk's pass drains, and each chunk adds a kernel tail + a barrier.
+        # Default 1: measured on 8 B200 (profiles/README.md) chunking never paid -- pass and combine are both latency-bound,
+        # so running them side by side only shares the SMs, and each chunk adds a kernel tail + a barrier.
         if item_chunks is None:
             item_chunks = int(os.environ.get("PMF_ITEM_CHUNKS", 1)) if self.world > 1 else 1
         self.item_chunks = max(1, min(int(item_chunks), self.n_items)) if self.world > 1 else 1
