@@ -39,8 +39,8 @@ int pmf_device_count(int* count);      /* fails (PMF_ECUDA) when no CUDA driver/
 int pmf_row_stride(int K);             /* smallest legal `ld` for K factors */
 /* Blocking device->host copy of `bytes` bytes (diagnostics / tests; synchronises the stream). */
 int pmf_copy_to_host(void* h_dst, const void* d_src, int64_t bytes, void* stream);
-/* Kernel-variant selection for experiments ("gamma_group", "gamma_unroll"; 0 = automatic).  Process-wide and not
- * synchronised: set before launching work, never while another thread is inside the library. */
+/* Kernel-variant selection for experiments ("gamma_group", "gamma_unroll", "gamma_chunk_reduce", "topn_growth"; 0 / -1 =
+ * automatic).  Per calling thread (thread-local): it affects only launches made by the thread that set it. */
 int pmf_tune(const char* key, int value);
 /* Asynchronous copy between device buffers by the copy engines (cudaMemcpyAsync, unified addressing: a pointer may be a
  * peer GPU's memory mapped into this process) -- used to stage per-rank row sums on their owner without occupying SMs. */

@@ -27,7 +27,7 @@
 
 namespace pmf {
 
-extern int g_tune_topn_growth;   // topn_fused.cu
+extern thread_local int g_tune_topn_growth;   // topn_fused.cu
 
 struct GammaArgs {
     const int4* seg_desc;   // segments in processing order: {row, start, end, partial slot or -1}
@@ -471,10 +471,10 @@ __global__ void __launch_bounds__(256) gamma_combine_kernel(const GammaArgs a, c
     gamma_row_update<G, V, MODE>(a, R, gl, group_mask<G>(lane), self, sa, sb, 0.f, false);
 }
 
-static int g_tune_interleave = 0;   // 1 = golden-ratio block interleave of the longest-first order (experiment)
-static int g_tune_group = 0;   // 0 = auto; else forced G for nvec <= 16 (8 or 16)
-static int g_tune_unroll = 0;  // 0 = auto; else forced U
-static int g_tune_chunk_reduce = -1;  // -1 = auto (by gathered-table size), 0 = per-rating dot reduction, 1 = chunk-wide butterfly
+static thread_local int g_tune_interleave = 0;   // 1 = golden-ratio block interleave of the longest-first order (experiment)
+static thread_local int g_tune_group = 0;   // 0 = auto; else forced G for nvec <= 16 (8 or 16)
+static thread_local int g_tune_unroll = 0;  // 0 = auto; else forced U
+static thread_local int g_tune_chunk_reduce = -1;  // -1 = auto (by gathered-table size), 0 = per-rating dot reduction, 1 = chunk-wide butterfly
 
 static uint32_t gcd_u32(uint32_t x, uint32_t y) {
     while (y) { const uint32_t t = x % y; x = y; y = t; }

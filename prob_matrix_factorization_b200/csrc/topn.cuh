@@ -242,7 +242,7 @@ struct TopnProblem {
     float* score_out;
     int32_t* stats;
 };
-extern int g_tune_topn_growth;   // 0 = auto (256 / n); else items covered per level = (1 + growth) x what was covered (pmf_tune)
+extern thread_local int g_tune_topn_growth;   // 0 = auto (256 / n); else items covered per level = (1 + growth) x what was covered (pmf_tune)
 bool topn_fused_supported(int32_t K, int32_t n);
 int64_t topn_fused_workspace_bytes(int64_t batch_rows, int32_t n_items, int32_t K);
 int topn_fused_run(const TopnProblem& p, void* workspace, int64_t workspace_bytes, cudaStream_t s);

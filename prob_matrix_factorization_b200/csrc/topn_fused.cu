@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(kRefineThreads) topn_refine_kernel(const Refin
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-int g_tune_topn_growth = 0;
+thread_local int g_tune_topn_growth = 0;
 
 static int64_t pad_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
