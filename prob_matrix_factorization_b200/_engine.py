@@ -270,10 +270,13 @@ class GammaEngine:
     SDDMM+reduce passes per iteration.  Each pass visits its tiles (ratings.py) in turn; on several
     GPUs the item pass ends with the cross-rank combine of the row sums:
 
-      "mc"   (default) pmf_gamma_combine: multimem.ld_reduce adds the ranks' sums inside the NVSwitch, the owner
-             updates the row and multimem.st replicates it; the item rows are processed in `item_chunks` chunks so
-             that the combine of one chunk (side stream) overlaps the pass over the next;
-      "nccl" unfused baseline: NCCL all-reduce of the sums, every rank updates every row.
+      "mc"   pmf_gamma_combine: multimem.ld_reduce adds the ranks' sums inside the NVSwitch, the owner updates the row
+             and multimem.st replicates it (default beyond 2 GPUs);
+      "ce"   pmf_gamma_combine_staged: the sums are copied to their owner by the copy engines and added in rank order
+             (default at 2 GPUs); update + replication as "mc";
+      "nccl" unfused baseline: NCCL all-reduce of the sums, every rank updates every row (fall-back without multicast).
+    The item rows can be processed in `item_chunks` chunks, the exchange of one chunk (side stream) next to the pass over
+    the next -- measured not to pay with the present kernels (default 1 chunk).
     """
 
     def __init__(self, ratings: DeviceRatings, K, user_shape, item_shape, user_rate=None, item_rate=None,
