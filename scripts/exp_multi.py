@@ -1,5 +1,6 @@
 """Experiment driver (not part of the product): one torchrun launch, many (seg_len, tuning) combos on C5.
-Usage: torchrun ... scripts/exp_multi.py "256:gamma_interleave=0" "256:gamma_interleave=1" ..."""
+Usage: torchrun ... scripts/exp_multi.py "256:gamma_interleave=0" ":exchange=ce" ":exchange=mc" ...
+(combo = [seg_len]:[key=value,...]; exchange = mc | ce | nccl; PMF_ITEM_CHUNKS / PMF_USER_PASS_TILES from the environment)"""
 import os
 import sys
 import time
@@ -25,7 +26,8 @@ def main():
     for combo in sys.argv[1:]:
         seg, _, tune = combo.partition(":")
         for k in ("gamma_interleave", "gamma_group", "gamma_unroll"):
-            _cabi.call("pmf_tune", k.encode(), -1 if k == "gamma_interleave" else 0)
+            _cabi.call("pmf_tune", k.encode(), 0)
+        os.environ.pop("PMF_EXCHANGE", None)
         for kv in filter(None, tune.split(",")):
             k, v = kv.split("=")
             if k == "exchange":
@@ -52,7 +54,7 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(f"EXP [{eng.exchange}] {combo:40s} seg_len={eng.r.by_user.seg_len:5d} user {tt[0]:.3f} item {tt[1]:.3f} step {tt[2]:.3f} ms "
+            print(f"EXP [{eng.exchange}] {combo:40s} seg_len={eng.r.seg_len_user}/{eng.r.seg_len_item} user {tt[0]:.3f} item {tt[1]:.3f} step {tt[2]:.3f} ms "
                   f"-> {w.nnz / (tt[2].item() * 1e-3):.3e} nnz*it/s", flush=True)
         eng.close()
         m._engine = None
